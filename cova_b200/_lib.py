@@ -1,0 +1,97 @@
+"""ctypes binding of libcova_b200.so (include/cova_b200.h).  Fails loudly if the library is missing:
+there is no Python / CPU fallback for any of the entry points."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcova_b200.so")
+
+OK, DROPPED = 0, 1
+E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE = -1, -2, -3, -4, -5, -6, -7
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED = 0x100, 0x200
+
+
+class CovaError(RuntimeError):
+    def __init__(self, code: int, detail: str):
+        super().__init__(f"cova_b200 error {code}: {detail}")
+        self.code = code
+
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_f32p = ctypes.POINTER(ctypes.c_float)
+_szp = ctypes.POINTER(ctypes.c_size_t)
+_vp = ctypes.c_void_p
+_vpp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); every symbol include/cova_b200.h declares
+SIGNATURES = {
+    "cova_version": (ctypes.c_char_p, []),
+    "cova_strerror": (ctypes.c_char_p, [ctypes.c_int]),
+    "cova_last_error": (ctypes.c_char_p, []),
+    "cova_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "cova_metapreprocess_new": (ctypes.c_int, [_vpp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    "cova_metapreprocess_free": (None, [_vp]),
+    "cova_metapreprocess_set_gamma": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "cova_metapreprocess_out_caps": (ctypes.c_int, [_vp, _u32p, _u32p, _szp]),
+    "cova_metapreprocess_transform": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]),
+    "cova_bboxcc_new": (ctypes.c_int, [_vpp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    "cova_bboxcc_free": (None, [_vp]),
+    "cova_bboxcc_set_cc_threshold": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "cova_bboxcc_get_cc_threshold": (ctypes.c_int, [_vp, _u32p]),
+    "cova_bboxcc_max_out_size": (ctypes.c_size_t, [_vp]),
+    "cova_bboxcc_transform_ip": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _szp]),
+    "cova_bboxcc_labels": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp, _vp, _i32p]),
+    "cova_pipeline_new": (ctypes.c_int, [_vpp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32]),
+    "cova_pipeline_free": (None, [_vp]),
+    "cova_pipeline_set_cc_threshold": (ctypes.c_int, [_vp, ctypes.c_uint32]),
+    "cova_pipeline_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "cova_pipeline_n_windows": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _u32p]),
+    "cova_pipeline_load_frames": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]),
+    "cova_pipeline_tensorise": (ctypes.c_int, [_vp]),
+    "cova_pipeline_blobnet": (ctypes.c_int, [_vp]),
+    "cova_pipeline_ccl": (ctypes.c_int, [_vp]),
+    "cova_pipeline_run": (ctypes.c_int, [_vp]),
+    "cova_pipeline_sync": (ctypes.c_int, [_vp]),
+    "cova_pipeline_fetch_boxes": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp]),
+    "cova_pipeline_process_host": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p]),
+    "cova_pipeline_load_masks": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_int]),
+    "cova_pipeline_read_stacked": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "cova_pipeline_read_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "cova_pipeline_read_logits": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "cova_pipeline_read_activation": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _u32p]),
+    "cova_pipeline_run_layer": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32]),
+    "cova_pipeline_launch_count": (ctypes.c_int, [_vp, _u64p]),
+    "cova_pipeline_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "cova_pipeline_last_timings": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t, _f32p, _u32p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (built in-tree by cova_b200/build.py).  Raises if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(f"{SO_PATH} is missing: run `python -m cova_b200.build` (nvcc, sm_100a). "
+                              "cova_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise CovaError(rc, load().cova_last_error().decode(errors="replace"))
+    return rc

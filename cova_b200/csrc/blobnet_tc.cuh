@@ -1,0 +1,499 @@
+// BlobNet layers as tcgen05 / TMEM implicit GEMMs ("shift-GEMM"), sm_100a.
+//
+// Every layer is   D[pos, n] = sum_{tap} sum_{c} A[pos + shift(tap), c] * W[tap][c][n]
+// over 128-position tiles of the phase-plane layout (common.cuh): because a spatial shift is a
+// constant row offset there, the A operand of every tap is just a different START ADDRESS into one
+// shared-memory strip that a bulk-async copy (cp.async.bulk, SASS UBLKCP) brought in once - no im2col,
+// no re-load per tap.  Operands use the canonical K-major no-swizzle core-matrix layout
+// (8 rows x 16 bytes; SBO = 128 B between 8-row groups, LBO = distance between the two 8-channel
+// halves of a K=16 step).  Four accumulators per tile live in TMEM, one per output phase:
+//   encoder: the four conv outputs a 2x2 max-pool window needs -> bias+ReLU+BN+max are done in
+//            registers straight out of TMEM, then PointWiseTN across the 4 frames of a window, which
+//            sit in 4 adjacent TMEM lanes (quad shuffles);
+//   decoder: the four input phases of a stride-2 transposed conv; N = 4 output parities x Cout.
+// Warp roles: warp 0 = bulk-copy producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Persistent CTAs, one per SM.
+//
+// Reference for the math: utils/model/encoder.py:33-76, pointwise.py:10-26, decoder.py:5-64,106-134.
+#pragma once
+#include "common.cuh"
+#include "weights_pack.cuh"
+
+namespace cova {
+namespace tc {
+
+constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2;
+constexpr int kMaxStage = 4;
+constexpr int kThreads = 192;
+
+struct LayerParams {
+    const uint4 *in; Geom gin;
+    uint4 *out; Geom gout;             // ENC: Tn=4 output (may be null); DEC: next concat buffer
+    uint4 *out2; Geom gout2;           // ENC: Tn=1 copy of t=0 (skip / dec0 input)
+    int out2_cb;                       // ENC: channel-block offset of the skip inside the concat buffer
+    const uint4 *wpack;                // B blocks (fp16), per N-half contiguous
+    const float *epi;                  // epilogue constants
+    float tn_w1[16], tn_w2[16];        // ENC: PointWiseTN matrices [T_in][T_out]
+    int N;                             // windows in this batch
+    int n_tiles, n_groups;             // 128-position tiles / groups of TPS tiles
+    int Ls;                            // strip rows per (cb, phase) in one stage = TPS*128 + 2*halo
+    int n_stage;                       // ring depth actually used (<= kMaxStage)
+    int w_bytes;                       // bytes of B blocks per N-half
+    int nsplit;                        // DEC: N split over CTAs (dec0: 2)
+    int Ht, Wt, crop_t, crop_l;        // DEC/HEAD: target extent and crop
+    uint8_t *mask; float *logits;      // HEAD
+    unsigned int *watchdog;            // set to a non-zero code if a barrier wait times out
+};
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a descriptor / protocol bug must fail the launch, never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int *watchdog, unsigned int code) {
+    for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin) {
+        if (spin > (1u << 22)) {
+            if (watchdog) atomicExch(watchdog, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle, sm_100 version bit (cute SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
+
+__host__ __device__ constexpr int fdiv2(int v) { return v >= 0 ? v / 2 : -((1 - v) / 2); }
+__host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int MODE_, int CIN_CB_, int NCOLS_, int TPS_, int KCH_, int COUT_>
+struct Cfg {
+    static constexpr int MODE = MODE_, CIN_CB = CIN_CB_, NCOLS = NCOLS_, TPS = TPS_, KCH = KCH_, COUT = COUT_;
+    static constexpr int NKC = CIN_CB / KCH;
+    static constexpr int COLS_TILE = 4 * NCOLS;
+    static constexpr int NSLOT = (512 / COLS_TILE) < 4 ? (512 / COLS_TILE) : 4;
+    static constexpr int TMEM_COLS = pow2_cols(NSLOT * COLS_TILE);
+    static constexpr bool ENC1 = (MODE == MODE_ENC && CIN_CB == 1);
+    static constexpr int NTAP = MODE == MODE_ENC ? 9 : 4;
+    static constexpr int KP = ENC1 ? 1 : KCH / 2;                        // K=16 steps per tap inside a stage
+    static constexpr int BLOCKS = ENC1 ? 20 : NTAP * (CIN_CB / 2);       // B blocks per N-half
+    static_assert(NKC == 1 || TPS == 1, "accumulating over k-chunks needs one tile per stage");
+    static_assert(ENC1 || (KCH % 2 == 0), "a K=16 step spans two channel blocks");
+    static_assert(COLS_TILE <= 512, "accumulators exceed TMEM");
+};
+
+struct SmemPlan {
+    uint32_t w_off, stage_off, stage_bytes, epi_off, bar_off, total;
+};
+template <class C>
+__host__ __device__ inline SmemPlan plan_smem(int Ls, int n_stage, int w_bytes, int epi_floats) {
+    SmemPlan s;
+    s.w_off = 0;
+    s.stage_off = (uint32_t)((w_bytes + 127) / 128 * 128);
+    s.stage_bytes = (uint32_t)(C::KCH * 4 * Ls * 16);
+    s.epi_off = s.stage_off + (uint32_t)n_stage * s.stage_bytes;
+    s.bar_off = s.epi_off + (uint32_t)((epi_floats * 4 + 15) / 16 * 16);
+    s.total = s.bar_off + 8 * (2 * kMaxStage + 2 * 4 + 1) + 16;
+    return s;
+}
+template <class C>
+__host__ __device__ constexpr int epi_floats() {
+    return C::MODE == MODE_ENC ? 3 * C::COUT + 32 : (C::MODE == MODE_DEC ? 2 * C::COUT : 4);
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issue
+// All MMAs of one tile for one stage (k-chunk kc).  Fully unrolled: plane/shift of every tap are
+// compile-time, only P, Tn, Ls are runtime.
+template <class C>
+__device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_addr, uint32_t w_addr, uint32_t d_tmem,
+                                           int tile_in_stage, int kc, uint32_t idesc) {
+    const int Ls = p.Ls, P = p.gin.P, Tn = p.gin.Tn;
+    const uint32_t a_lbo = C::ENC1 ? 0u : (uint32_t)(4 * Ls * 16);
+    const uint64_t bdesc0 = make_desc(w_addr, (uint32_t)C::NCOLS * 16u, 128u);
+    const int row0 = p.gin.halo + tile_in_stage * kTileM;
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+        const int pa = ph >> 1, pb = ph & 1;
+        const uint32_t d = d_tmem + (uint32_t)(ph * C::NCOLS);
+        if constexpr (C::ENC1) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const Enc1Step s = enc1_step(pa, j);
+                const int plane0 = (((pa + s.dy0) & 1) << 1) | ((pb + s.dx0) & 1);
+                const int r0 = plane0 * Ls + row0 + (fdiv2(pa + s.dy0) * P + fdiv2(pb + s.dx0)) * Tn;
+                int lbo_rows = Tn;   // unused second half: any readable row
+                if (s.dy1 != 9) {
+                    const int plane1 = (((pa + s.dy1) & 1) << 1) | ((pb + s.dx1) & 1);
+                    const int r1 = plane1 * Ls + row0 + (fdiv2(pa + s.dy1) * P + fdiv2(pb + s.dx1)) * Tn;
+                    lbo_rows = r1 - r0;
+                }
+                const uint64_t adesc = make_desc(stage_addr + (uint32_t)r0 * 16u, (uint32_t)lbo_rows * 16u, 128u);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((ph * 5 + j) * C::NCOLS * 2);   // block = NCOLS*32 B = NCOLS*2 x 16 B
+                umma_f16(d, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+            }
+        } else {
+#pragma unroll
+            for (int tp = 0; tp < C::NTAP; tp++) {
+                int plane, sy, sx;
+                if constexpr (C::MODE == MODE_ENC) {
+                    const int dy = tp / 3 - 1, dx = tp % 3 - 1;
+                    plane = (((pa + dy) & 1) << 1) | ((pb + dx) & 1);
+                    sy = fdiv2(pa + dy); sx = fdiv2(pb + dx);
+                } else {
+                    const int a = tp >> 1, b = tp & 1;
+                    plane = (((pa - a) & 1) << 1) | ((pb - b) & 1);
+                    sy = fdiv2(pa - a); sx = fdiv2(pb - b);
+                }
+                const int r0 = plane * Ls + row0 + (sy * P + sx) * Tn;
+#pragma unroll
+                for (int kpl = 0; kpl < C::KP; kpl++) {
+                    const uint64_t adesc = make_desc(stage_addr + (uint32_t)((2 * kpl * 4) * Ls + r0) * 16u, a_lbo, 128u);
+                    const int block = tp * (C::CIN_CB / 2) + kc * C::KP + kpl;
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(block * C::NCOLS * 2);
+                    umma_f16(d, adesc, bdesc, idesc, (kc > 0 || tp > 0 || kpl > 0) ? 1u : 0u);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int lane) {
+    const Geom &gi = p.gin;
+    const int t = pp & 3;
+    const int qq = pp >> 2;
+    const int n = qq / gi.S;
+    const int r = qq - n * gi.S;
+    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const bool valid = n < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);
+    const int Y = y2 + (gi.H & 1), X = x2 + (gi.W & 1);          // zero-pad top / left when odd (encoder.py:68-76)
+    const int pho = ((Y & 1) << 1) | (X & 1);
+    long long row1 = 0, row2 = 0;
+    if (valid) {
+        if (p.out) row1 = geom_row(p.gout, 0, pho, geom_pos(p.gout, n, Y >> 1, X >> 1, t));
+        if (p.out2) row2 = geom_row(p.gout2, p.out2_cb, pho, geom_pos(p.gout2, n, Y >> 1, X >> 1, 0));
+    }
+    const float *bias = epi, *scale = epi + C::COUT, *shift = epi + 2 * C::COUT, *w2s = epi + 3 * C::COUT + 16;
+    float w2c[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) w2c[m] = w2s[m * 4 + t];          // column t of W2
+    const int qbase = lane & ~3;
+#pragma unroll 1
+    for (int cb = 0; cb < C::COUT / 8; cb++) {
+        uint32_t v[4][8];
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
+        tmem_wait_ld();
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c = cb * 8 + j;
+            const float b = bias[c], s = scale[c], sh = shift[c];
+            float m = fmaf(fmaxf(__uint_as_float(v[0][j]) + b, 0.f), s, sh);                  // ReLU -> BN
+#pragma unroll
+            for (int ph = 1; ph < 4; ph++) m = fmaxf(m, fmaf(fmaxf(__uint_as_float(v[ph][j]) + b, 0.f), s, sh));   // MaxPool
+            // PointWiseTN: the 4 frames of this window position are the 4 lanes of this quad
+            float xs[4];
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++) xs[ti] = __shfl_sync(0xffffffffu, m, qbase + ti);
+            float h2 = 0.f;
+#pragma unroll
+            for (int mm = 0; mm < 4; mm++) {
+                float h1 = 0.f;
+#pragma unroll
+                for (int ti = 0; ti < 4; ti++) h1 = fmaf(xs[ti], p.tn_w1[ti * 4 + mm], h1);
+                h2 = fmaf(fmaxf(h1, 0.f), w2c[mm], h2);
+            }
+            o[j] = fmaxf(m + fmaxf(h2, 0.f), 0.f);
+        }
+        if (valid) {
+            uint4 row;
+            row.x = pack_half2(o[0], o[1]); row.y = pack_half2(o[2], o[3]);
+            row.z = pack_half2(o[4], o[5]); row.w = pack_half2(o[6], o[7]);
+            if (p.out) p.out[row1 + (long long)cb * 4 * p.gout.Lp] = row;
+            if (p.out2 && t == 0) p.out2[row2 + (long long)cb * 4 * p.gout2.Lp] = row;
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int half) {
+    const Geom &gi = p.gin;
+    const int n = pp / gi.S;
+    const int r = pp - n * gi.S;
+    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    constexpr int PARN = C::NCOLS / C::COUT;   // output parities handled by this CTA
+    const float *scale = epi, *offs = epi + C::COUT;
+#pragma unroll 1
+    for (int ph = 0; ph < 4; ph++) {
+        const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);   // position in the (Hin+1) x (Win+1) sub-pixel grid
+        const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
+#pragma unroll 1
+        for (int pl = 0; pl < PARN; pl++) {
+            const int par = half * PARN + pl;
+            const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
+            const bool valid = vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt;
+            long long row = 0;
+            if (valid) row = geom_row(p.gout, 0, ((Y & 1) << 1) | (X & 1), geom_pos(p.gout, n, Y >> 1, X >> 1, 0));
+#pragma unroll
+            for (int cb = 0; cb < C::COUT / 8; cb++) {
+                uint32_t v[8];
+                tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + pl * C::COUT + cb * 8), v);
+                tmem_wait_ld();
+                if (valid) {
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        o[j] = fmaxf(fmaf(__uint_as_float(v[j]), scale[cb * 8 + j], offs[cb * 8 + j]), 0.f);   // bias+BN, then the consumer's ReLU
+                    uint4 rw;
+                    rw.x = pack_half2(o[0], o[1]); rw.y = pack_half2(o[2], o[3]);
+                    rw.z = pack_half2(o[4], o[5]); rw.w = pack_half2(o[6], o[7]);
+                    p.out[row + (long long)cb * 4 * p.gout.Lp] = rw;
+                }
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_head(const LayerParams &p, const float *epi, uint32_t taddr, int pp) {
+    const Geom &gi = p.gin;
+    const int n = pp / gi.S;
+    const int r = pp - n * gi.S;
+    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const float c0 = epi[0];
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+        uint32_t v[4];
+        tmem_ld4(taddr + (uint32_t)(ph * C::NCOLS), v);
+        tmem_wait_ld();
+        const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);
+        const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
+#pragma unroll
+        for (int par = 0; par < 4; par++) {
+            const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
+            if (vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt) {
+                const float z = __uint_as_float(v[par]) + c0;
+                const size_t o = ((size_t)n * p.Ht + Y) * p.Wt + X;
+                p.mask[o] = z > 0.f ? 1 : 0;      // sigmoid(z) > 0.5 (nvinfer threshold), +1 of maskcopy folded
+                if (p.logits) p.logits[o] = z;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <class C>
+__global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_constant__ LayerParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const SmemPlan sp = plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>());
+    const uint32_t smem_base = smem_u32(smem);
+    float *epi = reinterpret_cast<float *>(smem + sp.epi_off);
+    const uint32_t bar0 = smem_base + sp.bar_off;
+    auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(kMaxStage + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kMaxStage + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kMaxStage + 4 + s); };
+    const uint32_t w_bar = bar0 + 8u * (uint32_t)(2 * kMaxStage + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + sp.bar_off + 8 * (2 * kMaxStage + 9));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
+    const int half = (int)blockIdx.x % nsplit;
+    const int cta = (int)blockIdx.x / nsplit, n_cta = (int)gridDim.x / nsplit;
+
+    // epilogue constants -> smem (generic proxy)
+    for (int i = threadIdx.x; i < epi_floats<C>(); i += kThreads) {
+        float v;
+        if (C::MODE == MODE_ENC && i >= 3 * C::COUT) v = (i - 3 * C::COUT < 16) ? p.tn_w1[i - 3 * C::COUT] : p.tn_w2[i - 3 * C::COUT - 16];
+        else v = p.epi[i];
+        epi[i] = v;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxStage; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 4; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: weights once, then one strip per (group, k-chunk) =====
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
+            bulk_g2s(smem_base + sp.w_off, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)half * p.w_bytes,
+                     (uint32_t)p.w_bytes, w_bar);
+            uint32_t it = 0;
+            for (int g = cta; g < p.n_groups; g += n_cta) {
+                const long long pos0 = p.gin.guard + (long long)g * C::TPS * kTileM - p.gin.halo;
+                for (int kc = 0; kc < C::NKC; kc++, it++) {
+                    const int s = (int)(it % (uint32_t)p.n_stage);
+                    mbar_wait(empty_bar(s), ((it / (uint32_t)p.n_stage) & 1u) ^ 1u, p.watchdog, 1u);
+                    mbar_expect_tx(full_bar(s), sp.stage_bytes);
+                    const uint32_t dst0 = smem_base + sp.stage_off + (uint32_t)s * sp.stage_bytes;
+#pragma unroll 1
+                    for (int cbi = 0; cbi < C::KCH; cbi++)
+#pragma unroll
+                        for (int ph = 0; ph < 4; ph++)
+                            bulk_g2s(dst0 + (uint32_t)((cbi * 4 + ph) * p.Ls) * 16u,
+                                     p.in + geom_row(p.gin, kc * C::KCH + cbi, ph, pos0), (uint32_t)p.Ls * 16u, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(C::NCOLS);
+            mbar_wait(w_bar, 0u, p.watchdog, 2u);
+            uint32_t it = 0, tile_it = 0;
+            for (int g = cta; g < p.n_groups; g += n_cta) {
+                const uint32_t tile_it0 = tile_it;
+                for (int kc = 0; kc < C::NKC; kc++, it++) {
+                    const int s = (int)(it % (uint32_t)p.n_stage);
+                    mbar_wait(full_bar(s), (it / (uint32_t)p.n_stage) & 1u, p.watchdog, 3u);
+                    tc_fence_after();
+                    const uint32_t stage_addr = smem_base + sp.stage_off + (uint32_t)s * sp.stage_bytes;
+                    tile_it = tile_it0;
+#pragma unroll 1
+                    for (int j = 0; j < C::TPS; j++) {
+                        if ((g * C::TPS + j) >= p.n_tiles) break;
+                        const int slot = (int)(tile_it % (uint32_t)C::NSLOT);
+                        if (kc == 0) {
+                            mbar_wait(tempty_bar(slot), ((tile_it / (uint32_t)C::NSLOT) & 1u) ^ 1u, p.watchdog, 4u);
+                            tc_fence_after();
+                        }
+                        issue_tile<C>(p, stage_addr, smem_base + sp.w_off, tmem_base + (uint32_t)(slot * C::COLS_TILE), j, kc, idesc);
+                        if (kc == C::NKC - 1) umma_commit(tfull_bar(slot));
+                        tile_it++;
+                    }
+                    umma_commit(empty_bar(s));   // strip may be overwritten once these MMAs have read it
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> fused layer tail -> HBM =====
+        const int q = warp & 3;
+        uint32_t tile_it = 0;
+        for (int g = cta; g < p.n_groups; g += n_cta) {
+#pragma unroll 1
+            for (int j = 0; j < C::TPS; j++) {
+                const int tile = g * C::TPS + j;
+                if (tile >= p.n_tiles) break;
+                const int slot = (int)(tile_it % (uint32_t)C::NSLOT);
+                mbar_wait(tfull_bar(slot), (tile_it / (uint32_t)C::NSLOT) & 1u, p.watchdog, 5u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * C::COLS_TILE);
+                const int pp = tile * kTileM + q * 32 + lane;
+                if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, taddr, pp, lane);
+                else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half);
+                else epilogue_head<C>(p, epi, taddr, pp);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(slot));
+                tile_it++;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+constexpr int kSmemLimit = 227 * 1024;
+
+template <class C>
+inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &err) {
+    const long long mtot = (long long)p.N * p.gin.S * p.gin.Tn;
+    p.n_tiles = (int)((mtot + kTileM - 1) / kTileM);
+    p.n_groups = (p.n_tiles + C::TPS - 1) / C::TPS;
+    p.Ls = C::TPS * kTileM + 2 * p.gin.halo;
+    if (4 * p.Ls >= 16384) return false;                       // LBO field: 14 bits of 16-byte units
+    if (p.gin.guard + (long long)p.n_groups * C::TPS * kTileM + p.gin.halo > p.gin.Lp) return false;
+    const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
+    p.w_bytes = C::BLOCKS * C::NCOLS * 32;
+    // ring depth: as deep as fits, up to 2 strips (whole-K stages) or 4 (k-chunked stages)
+    const int target = C::NKC > 1 ? kMaxStage : 2;
+    for (p.n_stage = target; p.n_stage >= 1; p.n_stage--)
+        if (plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>()).total <= (uint32_t)kSmemLimit) break;
+    if (p.n_stage < 1) return false;
+    const SmemPlan sp = plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>());
+    err = cudaFuncSetAttribute(shiftgemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    if (err != cudaSuccess) return true;
+    int ctas = n_sms / nsplit;
+    if (ctas > p.n_groups) ctas = p.n_groups;
+    if (ctas < 1) ctas = 1;
+    shiftgemm_kernel<C><<<ctas * nsplit, kThreads, sp.total, st>>>(p);
+    err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace tc
+}  // namespace cova

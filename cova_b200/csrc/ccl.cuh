@@ -1,0 +1,199 @@
+// Connected-component labelling + bounding boxes + bincode, one CTA per mask, entirely in shared memory.
+//
+// Reference: cova-rs/gst-plugins/src/bboxcc/process.rs:5-49 (cv::connectedComponentsWithStats, 8-connectivity,
+// CV_32S; keep CC_STAT_AREA >= threshold; Bbox::new(left, top, width, height)) and
+// cova-rs/bbox/src/bbox.rs:17-29,84-86 (area = width*height; bincode: u64 count + 24 bytes per box).
+//
+// Design (not OpenCV's two-pass scan): the mask is reduced to one 4-bit code per 2x2-aligned block
+// (all pixels of a 2x2 block are mutually 8-adjacent, so a block is the natural union-find node).
+// Blocks are merged with a lock-free atomicMin union-find in shared memory; because links always go
+// from the larger to the smaller block index, a component's root IS its first block in raster order,
+// which is exactly OpenCV's label order - so ranking the roots with a
+// block-wide prefix sum reproduces the reference's label numbers and box order with no sort.
+#pragma once
+#include "common.cuh"
+
+namespace cova {
+
+struct CclArgs {
+    const uint8_t *masks;     // [n][H][W]
+    int H, W, nbx, nby;       // nbx = ceil(W/2), nby = ceil(H/2)
+    int area_thresh;          // u32 property reinterpreted as i32 like imp.rs:248
+    uint8_t *blob;            // bincode output arena
+    unsigned long long blob_cap;
+    unsigned long long *cursor;   // [0] bytes reserved so far, [1] overflow flag
+    unsigned long long *offsets;  // [n]
+    unsigned long long *lens;     // [n]
+    int32_t *labels;          // optional [n][H][W]
+    int32_t *stats;           // optional [n][(nb+1)*5]
+    int32_t *n_labels;        // optional [n]
+};
+
+__host__ __device__ inline size_t ccl_smem_bytes(int nb, int threads) {
+    // parent + 5 stat arrays (int) + codes (u8, padded) + warp scan scratch
+    return (size_t)nb * 6 * sizeof(int) + (size_t)((nb + 15) / 16) * 16 + (size_t)(threads / 32 + 4) * sizeof(int);
+}
+
+__device__ __forceinline__ int uf_find(volatile int *parent, int i) {
+    int p;
+    while ((p = parent[i]) != i) i = p;
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&parent[a], b);   // link the larger root under the smaller one
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void ccl_bbox_kernel(CclArgs A) {
+    extern __shared__ __align__(16) unsigned char ccl_smem[];
+    const int nb = A.nbx * A.nby;
+    int *parent = reinterpret_cast<int *>(ccl_smem);
+    int *minx = parent + nb, *miny = minx + nb, *maxx = miny + nb, *maxy = maxx + nb, *area = maxy + nb;
+    uint8_t *code = reinterpret_cast<uint8_t *>(area + nb);
+    int *scan = reinterpret_cast<int *>(code + ((nb + 15) / 16) * 16);
+    __shared__ unsigned long long s_off;
+
+    const int frame = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint8_t *m = A.masks + (size_t)frame * A.H * A.W;
+
+    // 1. 2x2 block codes: bit0 (0,0) bit1 (0,1) bit2 (1,0) bit3 (1,1)
+    for (int b = tid; b < nb; b += nt) {
+        int by = b / A.nbx, bx = b - by * A.nbx;
+        int y = 2 * by, x = 2 * bx;
+        const uint8_t *r0 = m + (size_t)y * A.W + x;
+        bool x1 = x + 1 < A.W, y1 = y + 1 < A.H;
+        int c = (__ldg(r0) != 0) ? 1 : 0;
+        if (x1 && __ldg(r0 + 1) != 0) c |= 2;
+        if (y1 && __ldg(r0 + A.W) != 0) c |= 4;
+        if (x1 && y1 && __ldg(r0 + A.W + 1) != 0) c |= 8;
+        code[b] = (uint8_t)c;
+        parent[b] = c ? b : -1;
+        minx[b] = 0x7fffffff; miny[b] = 0x7fffffff; maxx[b] = -1; maxy[b] = -1; area[b] = 0;
+    }
+    __syncthreads();
+
+    // 2. merge with the four raster-preceding neighbour blocks
+    for (int b = tid; b < nb; b += nt) {
+        int c = code[b];
+        if (!c) continue;
+        int by = b / A.nbx, bx = b - by * A.nbx;
+        if (bx > 0 && (c & 0x5) && (code[b - 1] & 0xA)) uf_union(parent, b, b - 1);           // west: my left col / its right col
+        if (by > 0) {
+            int u = b - A.nbx;
+            if ((c & 0x3) && (code[u] & 0xC)) uf_union(parent, b, u);                          // north: my top row / its bottom row
+            if (bx > 0 && (c & 0x1) && (code[u - 1] & 0x8)) uf_union(parent, b, u - 1);        // north-west corner
+            if (bx + 1 < A.nbx && (c & 0x2) && (code[u + 1] & 0x4)) uf_union(parent, b, u + 1);  // north-east corner
+        }
+    }
+    __syncthreads();
+
+    // 3. flatten + per-root statistics
+    for (int b = tid; b < nb; b += nt) {
+        int c = code[b];
+        if (!c) continue;
+        int r = uf_find(parent, b);
+        parent[b] = r;
+        int by = b / A.nbx, bx = b - by * A.nbx;
+        int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
+        int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
+        atomicMin(&minx[r], x0); atomicMax(&maxx[r], x1);
+        atomicMin(&miny[r], y0); atomicMax(&maxy[r], y1);
+        atomicAdd(&area[r], __popc(c));
+    }
+    __syncthreads();
+
+    // 4. rank the roots in block-raster order: hi16 = all components, lo16 = components passing the filter
+    const int ipt = (nb + nt - 1) / nt;
+    const int b0 = min(tid * ipt, nb), b1 = min(b0 + ipt, nb);
+    int cnt = 0;
+    for (int b = b0; b < b1; b++)
+        if (parent[b] == b) cnt += 0x10000 + (area[b] >= A.area_thresh ? 1 : 0);
+    int incl = cnt;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) scan[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = nt >> 5;
+        int v = lane < nw ? scan[lane] : 0, s = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += u;
+        }
+        if (lane < nw) scan[lane] = s - v;   // exclusive warp offsets
+        if (lane == 31) scan[nw] = s;        // grand total
+    }
+    __syncthreads();
+    const int total = scan[nt >> 5];
+    const int n_all = total >> 16, n_keep = total & 0xffff;
+    int excl = scan[wid] + incl - cnt;
+
+    // 5. reserve the output range
+    const unsigned long long need = 8ull + 24ull * (unsigned long long)n_keep;
+    if (tid == 0) {
+        unsigned long long off = atomicAdd(A.cursor, need);
+        s_off = off;
+        A.offsets[frame] = off;
+        A.lens[frame] = need;
+        if (off + need > A.blob_cap) atomicExch(A.cursor + 1, 1ull);
+        if (A.n_labels) A.n_labels[frame] = n_all + 1;
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+    const bool fits = off + need <= A.blob_cap;
+    if (tid == 0 && fits) *reinterpret_cast<unsigned long long *>(A.blob + off) = (unsigned long long)n_keep;
+    int32_t *st = A.stats ? A.stats + (size_t)frame * (nb + 1) * 5 : nullptr;
+    if (st && tid < 5) st[tid] = 0;
+
+    // 6. emit boxes in label order; turn area[] into the root -> label map
+    int rank_all = excl >> 16, rank_keep = excl & 0xffff;
+    for (int b = b0; b < b1; b++) {
+        if (parent[b] != b) continue;
+        int x0 = minx[b], y0 = miny[b], w = maxx[b] - x0 + 1, h = maxy[b] - y0 + 1, ar = area[b];
+        rank_all++;
+        if (st) {
+            int32_t *s5 = st + (size_t)rank_all * 5;
+            s5[0] = x0; s5[1] = y0; s5[2] = w; s5[3] = h; s5[4] = ar;
+        }
+        if (ar >= A.area_thresh) {
+            if (fits) {
+                uint32_t *rec = reinterpret_cast<uint32_t *>(A.blob + off + 8 + 24ull * rank_keep);
+                float fw = (float)w, fh = (float)h;
+                rec[0] = __float_as_uint((float)x0);
+                rec[1] = __float_as_uint((float)y0);
+                rec[2] = __float_as_uint(fw);
+                rec[3] = __float_as_uint(fh);
+                rec[4] = __float_as_uint(fw * fh);   // bbox.rs:23
+                rec[5] = 0u;                         // track_id, timestamp, class_id, confidence = None
+            }
+            rank_keep++;
+        }
+        area[b] = rank_all;
+    }
+    if (!A.labels) return;
+    __syncthreads();
+    int32_t *lab = A.labels + (size_t)frame * A.H * A.W;
+    for (int p = tid; p < A.H * A.W; p += nt) {
+        int y = p / A.W, x = p - y * A.W;
+        int b = (y >> 1) * A.nbx + (x >> 1);
+        lab[p] = (__ldg(m + p) != 0) ? area[parent[b]] : 0;
+    }
+}
+
+inline int ccl_threads_for(int nb) { return nb <= 1024 ? 256 : (nb <= 4096 ? 512 : 1024); }
+
+}  // namespace cova

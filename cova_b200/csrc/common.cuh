@@ -1,0 +1,99 @@
+// Shared definitions of the cova_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cova_b200.h"
+
+namespace cova {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: nothing throws or aborts across the C ABI
+// ------------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+inline int set_err(int code, const char *fmt, const char *a = "", const char *b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define COVA_CUDA(expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return cova::set_err(COVA_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Activation layout in HBM ("phase planes").
+//
+// A logical activation [n][t][c][y][x] (n windows, t in [0,Tn), c channels, H x W) is stored as fp16
+// rows of 8 channels (16 bytes), one row per position, in 4 phase planes (a = y&1, b = x&1) per
+// channel block:
+//     row(cb, ph, pos)        = (cb*4 + ph) * Lp + pos                       [units of 16 bytes]
+//     pos(n, y2, x2, t)       = guard + ((n*S + y2*P + x2) * Tn + t)         y2 = y>>1, x2 = x>>1
+//     P = ceil(W/2) + 1, R = ceil(H/2) + 1, S = R*P
+// Every phase plane carries one shared zero column (x2 = Wh) and one shared zero row (y2 = Hh), so
+// that a spatial shift of the operand is a constant offset of `pos`: (dy2*P + dx2)*Tn.  A 3x3 "same"
+// convolution followed by 2x2 max-pooling, and a stride-2 transposed convolution, both become sums of
+// GEMMs over *contiguous* 128-position slices of these planes - no im2col.  T is interleaved
+// innermost so that the four frames of a window sit in four adjacent TMEM lanes (PointWiseTN).
+// Rows outside the logical extent are zero and are never written.
+// ------------------------------------------------------------------------------------------------
+struct Geom {
+    int H, W;        // logical extent
+    int Hh, Wh;      // phase-plane extent
+    int P, R, S;     // pitch, rows, positions per (window, phase)
+    int Tn;          // interleaved time planes: 4 (encoder side) or 1 (decoder side)
+    int CB;          // channel blocks (8 channels each)
+    int halo;        // (P+1)*Tn : largest |shift| any operand uses
+    long long guard; // zero rows in front of position 0 (>= halo)
+    long long Lp;    // rows per (cb, phase) plane
+    int N;           // window capacity
+};
+
+constexpr int kTileM = 128;
+constexpr int kGroupAlign = 8 * kTileM;  // plane length slack so that any tiles-per-stage <= 8 may over-read
+
+inline Geom make_geom(int H, int W, int C, int Tn, int N) {
+    Geom g;
+    g.H = H; g.W = W;
+    g.Hh = (H + 1) / 2; g.Wh = (W + 1) / 2;
+    g.P = g.Wh + 1; g.R = g.Hh + 1; g.S = g.R * g.P;
+    g.Tn = Tn; g.CB = (C + 7) / 8;
+    g.halo = (g.P + 1) * Tn;
+    g.guard = ((g.halo + 7) / 8) * 8;
+    long long m = (long long)N * g.S * Tn;
+    m = ((m + kGroupAlign - 1) / kGroupAlign) * kGroupAlign;
+    g.Lp = g.guard + m + g.guard;
+    g.N = N;
+    return g;
+}
+__host__ __device__ inline long long geom_rows(const Geom &g) { return (long long)g.CB * 4 * g.Lp; }
+__host__ __device__ inline long long geom_pos(const Geom &g, int n, int y2, int x2, int t) {
+    return g.guard + ((long long)n * g.S + (long long)y2 * g.P + x2) * g.Tn + t;
+}
+__host__ __device__ inline long long geom_row(const Geom &g, int cb, int ph, long long pos) {
+    return ((long long)cb * 4 + ph) * g.Lp + pos;
+}
+// row index (16-byte units) of logical element (n, t, cb, y, x)
+__host__ __device__ inline long long geom_row_of(const Geom &g, int n, int t, int cb, int y, int x) {
+    return geom_row(g, cb, ((y & 1) << 1) | (x & 1), geom_pos(g, n, y >> 1, x >> 1, t));
+}
+
+// BlobNet architecture constants (reference utils/train-blobnet.py:57-69)
+constexpr int kT = 4;
+constexpr int kEncCin[4] = {3, 16, 32, 64};
+constexpr int kEncCout[4] = {16, 32, 64, 128};
+constexpr int kDecCin[4] = {128, 128, 64, 32};
+constexpr int kDecCout[4] = {64, 32, 16, 16};
+constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default (reference encoder.py:45-48)
+
+struct alignas(16) Row8 {  // one 16-byte row: 8 fp16 channels
+    __half v[8];
+};
+
+}  // namespace cova

@@ -1,0 +1,863 @@
+// C ABI of libcova_b200.so (see include/cova_b200.h).  One translation unit: kernels + host plumbing.
+// There is NO CPU fallback anywhere in this file: without a CUDA device every constructor fails with
+// COVA_E_NODEVICE.
+#include <math.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "blobnet_simt.cuh"
+#include "blobnet_tc.cuh"
+#include "ccl.cuh"
+#include "common.cuh"
+#include "tensorise.cuh"
+#include "weights_pack.cuh"
+
+namespace cova {
+thread_local char g_err[512] = "";
+
+static int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return set_err(COVA_E_NODEVICE, "no CUDA device (%s); cova_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_err(COVA_E_INVAL, "device index out of range");
+    COVA_CUDA(cudaSetDevice(device));
+    return COVA_OK;
+}
+
+// newest-frame ring used by the metapreprocess element: slot of frame t-k = (head - k) mod T
+__global__ void __launch_bounds__(256) stack_ring_kernel(const uint32_t *__restrict__ ring, uint32_t *__restrict__ out,
+                                                         int words_per_frame, int T, int head) {
+    const int total = words_per_frame * T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int k = i / words_per_frame, e = i - k * words_per_frame;
+        int slot = (head - k + T) % T;
+        out[i] = ring[(size_t)slot * words_per_frame + e];
+    }
+}
+}  // namespace cova
+
+using namespace cova;
+
+// =================================================================================================
+// misc
+// =================================================================================================
+extern "C" const char *cova_version(void) { return "cova_b200 0.1 (sm_100a)"; }
+extern "C" const char *cova_last_error(void) { return g_err; }
+extern "C" const char *cova_strerror(int code) {
+    switch (code) {
+        case COVA_OK: return "ok";
+        case COVA_DROPPED: return "dropped (no output for this input)";
+        case COVA_E_INVAL: return "invalid argument";
+        case COVA_E_CUDA: return "CUDA error";
+        case COVA_E_NOMEM: return "out of memory";
+        case COVA_E_TOOSMALL: return "output buffer too small";
+        case COVA_E_WEIGHTS: return "bad weight container";
+        case COVA_E_UNSUPPORTED: return "unsupported configuration";
+        case COVA_E_NODEVICE: return "no CUDA device (no CPU fallback)";
+        default: return "unknown error";
+    }
+}
+extern "C" int cova_device_count(int *n) {
+    if (!n) return set_err(COVA_E_INVAL, "null argument");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+    *n = c;
+    return COVA_OK;
+}
+
+// =================================================================================================
+// metapreprocess element
+// =================================================================================================
+struct cova_metapreprocess {
+    int device;
+    uint32_t w_mb, h_mb, timestep, gamma, gamma_idx, n_prev;
+    int head;             // ring slot of the newest stored frame
+    size_t S;             // size_per_buf (imp.rs:233)
+    uint8_t *d_ring = nullptr, *d_out = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int cova_metapreprocess_new(cova_metapreprocess **out, int device, uint32_t width_px, uint32_t height_px,
+                                       uint32_t timestep, uint32_t gamma) {
+    if (!out) return set_err(COVA_E_INVAL, "null out");
+    *out = nullptr;
+    if (timestep < 1 || gamma < 1) return set_err(COVA_E_INVAL, "timestep and gamma are u32 >= 1");
+    if (width_px / 16 == 0 || height_px / 16 == 0) return set_err(COVA_E_INVAL, "frame smaller than one macroblock");
+    int rc = check_device(device);
+    if (rc) return rc;
+    auto *mp = new (std::nothrow) cova_metapreprocess();
+    if (!mp) return set_err(COVA_E_NOMEM, "host allocation failed");
+    mp->device = device;
+    mp->w_mb = width_px / 16;   // imp.rs:262-268: integer division
+    mp->h_mb = height_px / 16;
+    mp->timestep = timestep; mp->gamma = gamma; mp->gamma_idx = 0; mp->n_prev = 0; mp->head = -1;
+    mp->S = (size_t)mp->w_mb * mp->h_mb * 4;
+    cudaError_t e = cudaMalloc(&mp->d_ring, mp->S * timestep);
+    if (e == cudaSuccess) e = cudaMalloc(&mp->d_out, mp->S * timestep);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&mp->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cova_metapreprocess_free(mp);
+        return set_err(COVA_E_CUDA, "metapreprocess allocation: %s", cudaGetErrorString(e));
+    }
+    *out = mp;
+    return COVA_OK;
+}
+extern "C" void cova_metapreprocess_free(cova_metapreprocess *mp) {
+    if (!mp) return;
+    cudaSetDevice(mp->device);
+    if (mp->d_ring) cudaFree(mp->d_ring);
+    if (mp->d_out) cudaFree(mp->d_out);
+    if (mp->stream) cudaStreamDestroy(mp->stream);
+    delete mp;
+}
+extern "C" int cova_metapreprocess_set_gamma(cova_metapreprocess *mp, uint32_t gamma) {
+    if (!mp || gamma < 1) return set_err(COVA_E_INVAL, "gamma is a u32 >= 1");
+    mp->gamma = gamma;
+    return COVA_OK;
+}
+extern "C" int cova_metapreprocess_out_caps(const cova_metapreprocess *mp, uint32_t *width, uint32_t *height, size_t *size) {
+    if (!mp) return set_err(COVA_E_INVAL, "null handle");
+    if (width) *width = mp->w_mb;
+    if (height) *height = mp->h_mb * mp->timestep;
+    if (size) *size = mp->S * mp->timestep;
+    return COVA_OK;
+}
+extern "C" int cova_metapreprocess_transform(cova_metapreprocess *mp, const uint8_t *inbuf, size_t in_len, uint8_t *outbuf,
+                                             size_t out_cap) {
+    if (!mp || !inbuf) return set_err(COVA_E_INVAL, "null argument");
+    if (in_len < mp->S) return set_err(COVA_E_INVAL, "input buffer shorter than size_per_buf");
+    COVA_CUDA(cudaSetDevice(mp->device));
+    const int T = (int)mp->timestep;
+    // every branch of imp.rs:302-330 stores the incoming buffer as the newest one
+    const int slot = (mp->head + 1) % T;
+    COVA_CUDA(cudaMemcpyAsync(mp->d_ring + (size_t)slot * mp->S, inbuf, mp->S, cudaMemcpyHostToDevice, mp->stream));
+    mp->head = slot;
+    if (mp->n_prev < mp->timestep - 1) {          // imp.rs:302-305
+        mp->n_prev++;
+        COVA_CUDA(cudaStreamSynchronize(mp->stream));
+        return COVA_DROPPED;
+    }
+    if (mp->gamma_idx != 0) {                      // imp.rs:325-330
+        mp->gamma_idx--;
+        COVA_CUDA(cudaStreamSynchronize(mp->stream));
+        return COVA_DROPPED;
+    }
+    if (!outbuf || out_cap < mp->S * T) {
+        // keep element state consistent with "this buffer was consumed", but tell the caller
+        mp->gamma_idx = mp->gamma - 1;
+        cudaStreamSynchronize(mp->stream);
+        return set_err(COVA_E_TOOSMALL, "output buffer smaller than the RGBA stack");
+    }
+    const int words = (int)(mp->S / 4);
+    int blocks = std::min(1024, (words * T + 255) / 256);
+    stack_ring_kernel<<<blocks, 256, 0, mp->stream>>>(reinterpret_cast<const uint32_t *>(mp->d_ring),
+                                                      reinterpret_cast<uint32_t *>(mp->d_out), words, T, mp->head);
+    COVA_CUDA(cudaGetLastError());
+    COVA_CUDA(cudaMemcpyAsync(outbuf, mp->d_out, mp->S * T, cudaMemcpyDeviceToHost, mp->stream));
+    COVA_CUDA(cudaStreamSynchronize(mp->stream));
+    mp->gamma_idx = mp->gamma - 1;                 // imp.rs:323
+    return COVA_OK;
+}
+
+// =================================================================================================
+// CCL launch shared by the bboxcc element and the pipeline
+// =================================================================================================
+struct CclBuffers {
+    int H = 0, W = 0, nbx = 0, nby = 0, nb = 0, max_masks = 0;
+    uint8_t *d_masks = nullptr, *d_blob = nullptr;
+    size_t blob_cap = 0;
+    unsigned long long *d_cursor = nullptr, *d_offsets = nullptr, *d_lens = nullptr;
+    int32_t *d_labels = nullptr, *d_stats = nullptr, *d_nlabels = nullptr;
+    size_t smem = 0;
+    int threads = 0;
+};
+
+static int ccl_alloc(CclBuffers &b, int H, int W, int max_masks, bool own_masks) {
+    b.H = H; b.W = W; b.nbx = (W + 1) / 2; b.nby = (H + 1) / 2; b.nb = b.nbx * b.nby; b.max_masks = max_masks;
+    b.threads = ccl_threads_for(b.nb);
+    b.smem = ccl_smem_bytes(b.nb, b.threads);
+    if (b.smem > (size_t)tc::kSmemLimit || b.nb >= 0xFFFF)
+        return set_err(COVA_E_UNSUPPORTED, "mask grid too large for the shared-memory CCL kernel");
+    b.blob_cap = (size_t)max_masks * (8 + 24 * (size_t)b.nb);
+    if (own_masks) COVA_CUDA(cudaMalloc(&b.d_masks, (size_t)max_masks * H * W));
+    COVA_CUDA(cudaMalloc(&b.d_blob, b.blob_cap));
+    COVA_CUDA(cudaMalloc(&b.d_cursor, 2 * sizeof(unsigned long long)));
+    COVA_CUDA(cudaMalloc(&b.d_offsets, (size_t)max_masks * sizeof(unsigned long long)));
+    COVA_CUDA(cudaMalloc(&b.d_lens, (size_t)max_masks * sizeof(unsigned long long)));
+    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+    return COVA_OK;
+}
+static void ccl_free(CclBuffers &b, bool own_masks) {
+    if (own_masks && b.d_masks) cudaFree(b.d_masks);
+    if (b.d_blob) cudaFree(b.d_blob);
+    if (b.d_cursor) cudaFree(b.d_cursor);
+    if (b.d_offsets) cudaFree(b.d_offsets);
+    if (b.d_lens) cudaFree(b.d_lens);
+    if (b.d_labels) cudaFree(b.d_labels);
+    if (b.d_stats) cudaFree(b.d_stats);
+    if (b.d_nlabels) cudaFree(b.d_nlabels);
+}
+static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_threshold, bool want_labels, cudaStream_t st) {
+    if (n <= 0) return COVA_OK;
+    CclArgs a;
+    a.masks = d_masks; a.H = b.H; a.W = b.W; a.nbx = b.nbx; a.nby = b.nby;
+    a.area_thresh = (int)cc_threshold;   // `settings.cc_threshold as i32` (imp.rs:248)
+    a.blob = b.d_blob; a.blob_cap = b.blob_cap; a.cursor = b.d_cursor; a.offsets = b.d_offsets; a.lens = b.d_lens;
+    a.labels = want_labels ? b.d_labels : nullptr;
+    a.stats = want_labels ? b.d_stats : nullptr;
+    a.n_labels = want_labels ? b.d_nlabels : nullptr;
+    COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
+    ccl_bbox_kernel<<<n, b.threads, b.smem, st>>>(a);
+    COVA_CUDA(cudaGetLastError());
+    return COVA_OK;
+}
+
+// =================================================================================================
+// bboxcc element
+// =================================================================================================
+struct cova_bboxcc {
+    int device;
+    uint32_t width, height, cc_threshold;
+    CclBuffers b;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int cova_bboxcc_new(cova_bboxcc **out, int device, uint32_t width, uint32_t height, uint32_t cc_threshold) {
+    if (!out) return set_err(COVA_E_INVAL, "null out");
+    *out = nullptr;
+    if (!width || !height) return set_err(COVA_E_INVAL, "empty mask");
+    int rc = check_device(device);
+    if (rc) return rc;
+    auto *cc = new (std::nothrow) cova_bboxcc();
+    if (!cc) return set_err(COVA_E_NOMEM, "host allocation failed");
+    cc->device = device; cc->width = width; cc->height = height; cc->cc_threshold = cc_threshold;
+    rc = ccl_alloc(cc->b, (int)height, (int)width, 1, true);
+    if (rc == COVA_OK && cudaStreamCreateWithFlags(&cc->stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = set_err(COVA_E_CUDA, "stream creation failed");
+    if (rc) { cova_bboxcc_free(cc); return rc; }
+    *out = cc;
+    return COVA_OK;
+}
+extern "C" void cova_bboxcc_free(cova_bboxcc *cc) {
+    if (!cc) return;
+    cudaSetDevice(cc->device);
+    ccl_free(cc->b, true);
+    if (cc->stream) cudaStreamDestroy(cc->stream);
+    delete cc;
+}
+extern "C" int cova_bboxcc_set_cc_threshold(cova_bboxcc *cc, uint32_t t) {
+    if (!cc) return set_err(COVA_E_INVAL, "null handle");
+    cc->cc_threshold = t;
+    return COVA_OK;
+}
+extern "C" int cova_bboxcc_get_cc_threshold(const cova_bboxcc *cc, uint32_t *t) {
+    if (!cc || !t) return set_err(COVA_E_INVAL, "null argument");
+    *t = cc->cc_threshold;
+    return COVA_OK;
+}
+extern "C" size_t cova_bboxcc_max_out_size(const cova_bboxcc *cc) { return cc ? 8 + 24 * (size_t)cc->b.nb : 0; }
+
+extern "C" int cova_bboxcc_transform_ip(cova_bboxcc *cc, const uint8_t *mask, size_t mask_len, uint8_t *out, size_t out_cap,
+                                        size_t *out_len) {
+    if (!cc || !mask || !out_len) return set_err(COVA_E_INVAL, "null argument");
+    // process.rs:14-15: reshape(1, height) -> rows of len/height bytes; the element is configured per caps
+    if (mask_len != (size_t)cc->width * cc->height) return set_err(COVA_E_INVAL, "mask length != width*height of the caps");
+    COVA_CUDA(cudaSetDevice(cc->device));
+    COVA_CUDA(cudaMemcpyAsync(cc->b.d_masks, mask, mask_len, cudaMemcpyHostToDevice, cc->stream));
+    int rc = ccl_launch(cc->b, cc->b.d_masks, 1, cc->cc_threshold, false, cc->stream);
+    if (rc) return rc;
+    unsigned long long len = 0;
+    COVA_CUDA(cudaMemcpyAsync(&len, cc->b.d_lens, sizeof(len), cudaMemcpyDeviceToHost, cc->stream));
+    COVA_CUDA(cudaStreamSynchronize(cc->stream));
+    *out_len = (size_t)len;
+    if (!out || out_cap < len) return set_err(COVA_E_TOOSMALL, "serialized boxes need a larger buffer");
+    COVA_CUDA(cudaMemcpyAsync(out, cc->b.d_blob, len, cudaMemcpyDeviceToHost, cc->stream));
+    COVA_CUDA(cudaStreamSynchronize(cc->stream));
+    return COVA_OK;
+}
+
+extern "C" int cova_bboxcc_labels(cova_bboxcc *cc, const uint8_t *mask, size_t mask_len, int32_t *labels, int32_t *stats,
+                                  int32_t *n_labels) {
+    if (!cc || !mask || !labels || !stats || !n_labels) return set_err(COVA_E_INVAL, "null argument");
+    if (mask_len != (size_t)cc->width * cc->height) return set_err(COVA_E_INVAL, "mask length != width*height");
+    COVA_CUDA(cudaSetDevice(cc->device));
+    CclBuffers &b = cc->b;
+    if (!b.d_labels) {
+        COVA_CUDA(cudaMalloc(&b.d_labels, mask_len * sizeof(int32_t)));
+        COVA_CUDA(cudaMalloc(&b.d_stats, (size_t)(b.nb + 1) * 5 * sizeof(int32_t)));
+        COVA_CUDA(cudaMalloc(&b.d_nlabels, sizeof(int32_t)));
+    }
+    COVA_CUDA(cudaMemcpyAsync(b.d_masks, mask, mask_len, cudaMemcpyHostToDevice, cc->stream));
+    int rc = ccl_launch(b, b.d_masks, 1, cc->cc_threshold, true, cc->stream);
+    if (rc) return rc;
+    COVA_CUDA(cudaMemcpyAsync(n_labels, b.d_nlabels, sizeof(int32_t), cudaMemcpyDeviceToHost, cc->stream));
+    COVA_CUDA(cudaMemcpyAsync(labels, b.d_labels, mask_len * sizeof(int32_t), cudaMemcpyDeviceToHost, cc->stream));
+    COVA_CUDA(cudaStreamSynchronize(cc->stream));
+    COVA_CUDA(cudaMemcpyAsync(stats, b.d_stats, (size_t)(*n_labels) * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, cc->stream));
+    COVA_CUDA(cudaStreamSynchronize(cc->stream));
+    return COVA_OK;
+}
+
+// =================================================================================================
+// fused batch pipeline
+// =================================================================================================
+struct DevLayer {
+    uint4 *wpack = nullptr;
+    float *epi = nullptr;
+    int n_cols = 0;
+};
+
+struct cova_pipeline {
+    int device = 0, n_sms = 0;
+    uint32_t W = 0, H = 0, T = 0, gamma = 1, max_streams = 0, max_fps = 0, max_windows = 0, flags = 0, impl = 0;
+    uint32_t cc_threshold = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    size_t frame_bytes = 0;
+    uint8_t *d_frames = nullptr;
+    int *d_newest = nullptr;
+    uint32_t cur_streams = 0, cur_fps = 0, cur_windows = 0, table_streams = 0, table_fps = 0;
+    int sizes_h[5], sizes_w[5];          // extents: [0] input, [1..4] encoder outputs
+    Geom gx[4];                          // X0..X3 (Tn = 4): inputs of enc1..enc4
+    Geom gd[4];                          // D0in..D3in (Tn = 1): inputs of dec0..dec3
+    uint4 *x[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint4 *d[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *d_mask = nullptr, *d_stacked = nullptr;
+    float *d_logits = nullptr;
+    HostWeights hw;
+    float *d_wraw = nullptr;
+    DevLayer enc[4], dec[4];
+    CclBuffers ccl;
+    unsigned int *d_watchdog = nullptr;
+    unsigned long long *h_pinned = nullptr;   // cursor + overflow, then offsets/lens staging
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<std::string> names, last_names;
+    std::vector<float> last_ms;
+    size_t ev_used = 0;
+    uint64_t launches = 0;
+};
+
+static uint32_t windows_per_stream(uint32_t fps, uint32_t T, uint32_t gamma) {
+    if (fps < T) return 0;
+    return (fps - T) / gamma + 1;
+}
+
+static void prof_mark(cova_pipeline *p, const char *name) {
+    if (!p->profiling) return;
+    if (p->ev_used >= p->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        p->events.push_back(e);
+    }
+    cudaEventRecord(p->events[p->ev_used++], p->stream);
+    p->names.push_back(name);
+}
+
+template <typename T>
+static int dev_upload(T **dst, const void *src, size_t bytes) {
+    COVA_CUDA(cudaMalloc(dst, bytes));
+    COVA_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return COVA_OK;
+}
+
+static int upload_layer(DevLayer &dl, const PackedLayer *halves, int n_halves) {
+    size_t hb = halves[0].b.size() * sizeof(__half);
+    COVA_CUDA(cudaMalloc(&dl.wpack, hb * n_halves));
+    for (int h = 0; h < n_halves; h++)
+        COVA_CUDA(cudaMemcpy(reinterpret_cast<char *>(dl.wpack) + hb * h, halves[h].b.data(), hb, cudaMemcpyHostToDevice));
+    int rc = dev_upload(&dl.epi, halves[0].epi.data(), halves[0].epi.size() * sizeof(float));
+    dl.n_cols = halves[0].n_cols;
+    return rc;
+}
+
+extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb, uint32_t h_mb, uint32_t timestep,
+                                 uint32_t gamma, uint32_t max_streams, uint32_t max_fps, const void *weights,
+                                 size_t weights_len, uint32_t cc_threshold, uint32_t flags) {
+    if (!out) return set_err(COVA_E_INVAL, "null out");
+    *out = nullptr;
+    if (timestep != (uint32_t)kT) return set_err(COVA_E_UNSUPPORTED, "BlobNet is built for timestep = 4 (utils/train-blobnet.py:58)");
+    if (gamma < 1 || !max_streams || max_fps < timestep) return set_err(COVA_E_INVAL, "need gamma >= 1, max_streams >= 1, max_frames_per_stream >= timestep");
+    if (w_mb < 16 || h_mb < 16) return set_err(COVA_E_UNSUPPORTED, "macroblock grid must be at least 16x16 for four 2x poolings");
+    if ((flags & 0xffu) > COVA_IMPL_SIMT) return set_err(COVA_E_INVAL, "unknown implementation selector");
+    int rc = check_device(device);
+    if (rc) return rc;
+    auto *p = new (std::nothrow) cova_pipeline();
+    if (!p) return set_err(COVA_E_NOMEM, "host allocation failed");
+    p->device = device; p->W = w_mb; p->H = h_mb; p->T = timestep; p->gamma = gamma;
+    p->max_streams = max_streams; p->max_fps = max_fps; p->flags = flags; p->impl = flags & 0xffu;
+    p->cc_threshold = cc_threshold;
+    p->max_windows = max_streams * windows_per_stream(max_fps, timestep, gamma);
+    auto fail = [&](int code) { cova_pipeline_free(p); return code; };
+    if ((rc = parse_weights(weights, weights_len, p->hw))) return fail(rc);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(set_err(COVA_E_CUDA, "cudaGetDeviceProperties failed"));
+    p->n_sms = prop.multiProcessorCount;
+    if (p->impl == COVA_IMPL_TCGEN05 && prop.major != 10)
+        return fail(set_err(COVA_E_UNSUPPORTED, "the tcgen05 path needs an sm_100 device"));
+    if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_err(COVA_E_CUDA, "stream creation failed"));
+    p->stream = p->own_stream;
+
+    const int N = (int)p->max_windows;
+    p->sizes_h[0] = (int)h_mb; p->sizes_w[0] = (int)w_mb;
+    for (int i = 1; i <= 4; i++) { p->sizes_h[i] = (p->sizes_h[i - 1] + 1) / 2; p->sizes_w[i] = (p->sizes_w[i - 1] + 1) / 2; }
+    // encoder inputs (Tn = 4): X0 (8 ch incl. padding), X1 (16), X2 (32), X3 (64)
+    const int xc[4] = {8, 16, 32, 64};
+    for (int i = 0; i < 4; i++) p->gx[i] = make_geom(p->sizes_h[i], p->sizes_w[i], xc[i], kT, N);
+    // decoder inputs (Tn = 1): D0in = enc4 t0 (128 @ s4), D1in (128 @ s3), D2in (64 @ s2), D3in (32 @ s1)
+    for (int i = 0; i < 4; i++) p->gd[i] = make_geom(p->sizes_h[4 - i], p->sizes_w[4 - i], kDecCin[i], 1, N);
+    auto alloc_zero = [&](uint4 **ptr, const Geom &g) -> int {
+        size_t bytes = (size_t)geom_rows(g) * 16;
+        COVA_CUDA(cudaMalloc(ptr, bytes));
+        COVA_CUDA(cudaMemset(*ptr, 0, bytes));
+        return COVA_OK;
+    };
+    for (int i = 0; i < 4; i++) {
+        if ((rc = alloc_zero(&p->x[i], p->gx[i]))) return fail(rc);
+        if ((rc = alloc_zero(&p->d[i], p->gd[i]))) return fail(rc);
+    }
+    p->frame_bytes = (size_t)w_mb * h_mb * 4;
+    cudaError_t e = cudaMalloc(&p->d_frames, p->frame_bytes * max_streams * max_fps);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_newest, sizeof(int) * std::max(1, N));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_mask, (size_t)std::max(1, N) * w_mb * h_mb);
+    if (e == cudaSuccess) e = cudaMemset(p->d_mask, 0, (size_t)std::max(1, N) * w_mb * h_mb);
+    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_LOGITS)) e = cudaMalloc(&p->d_logits, sizeof(float) * (size_t)N * w_mb * h_mb);
+    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_STACKED)) e = cudaMalloc(&p->d_stacked, p->frame_bytes * timestep * (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_watchdog, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(p->d_watchdog, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost(&p->h_pinned, sizeof(unsigned long long) * (2 + 2 * (size_t)std::max(1, N)));
+    if (e != cudaSuccess) return fail(set_err(COVA_E_CUDA, "pipeline allocation: %s", cudaGetErrorString(e)));
+    p->ccl.d_masks = p->d_mask;
+    if ((rc = ccl_alloc(p->ccl, (int)h_mb, (int)w_mb, std::max(1, N), false))) return fail(rc);
+
+    // weights: raw fp32 for the validation kernels, packed fp16 operand blocks for the tcgen05 path
+    if ((rc = dev_upload(&p->d_wraw, p->hw.storage.data(), p->hw.storage.size() * sizeof(float)))) return fail(rc);
+    for (int i = 0; i < 4; i++) {
+        PackedLayer pl;
+        pack_encoder(p->hw, i, pl);
+        if ((rc = upload_layer(p->enc[i], &pl, 1))) return fail(rc);
+    }
+    for (int i = 0; i < 4; i++) {
+        const int nsplit = i == 0 ? 2 : 1;
+        PackedLayer pl[2];
+        for (int h = 0; h < nsplit; h++) pack_decoder(p->hw, i, nsplit, h, pl[h]);
+        if ((rc = upload_layer(p->dec[i], pl, nsplit))) return fail(rc);
+    }
+    *out = p;
+    return COVA_OK;
+}
+
+extern "C" void cova_pipeline_free(cova_pipeline *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 4; i++) {
+        if (p->x[i]) cudaFree(p->x[i]);
+        if (p->d[i]) cudaFree(p->d[i]);
+        if (p->enc[i].wpack) cudaFree(p->enc[i].wpack);
+        if (p->enc[i].epi) cudaFree(p->enc[i].epi);
+        if (p->dec[i].wpack) cudaFree(p->dec[i].wpack);
+        if (p->dec[i].epi) cudaFree(p->dec[i].epi);
+    }
+    if (p->d_frames) cudaFree(p->d_frames);
+    if (p->d_newest) cudaFree(p->d_newest);
+    if (p->d_mask) cudaFree(p->d_mask);
+    if (p->d_logits) cudaFree(p->d_logits);
+    if (p->d_stacked) cudaFree(p->d_stacked);
+    if (p->d_wraw) cudaFree(p->d_wraw);
+    if (p->d_watchdog) cudaFree(p->d_watchdog);
+    if (p->h_pinned) cudaFreeHost(p->h_pinned);
+    ccl_free(p->ccl, false);
+    for (auto e : p->events) cudaEventDestroy(e);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    cudaGetLastError();
+    delete p;
+}
+
+extern "C" int cova_pipeline_set_cc_threshold(cova_pipeline *p, uint32_t t) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    p->cc_threshold = t;
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_set_stream(cova_pipeline *p, void *s) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    p->stream = s ? reinterpret_cast<cudaStream_t>(s) : p->own_stream;
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_n_windows(const cova_pipeline *p, uint32_t n_streams, uint32_t fps, uint32_t *n) {
+    if (!p || !n) return set_err(COVA_E_INVAL, "null argument");
+    *n = n_streams * windows_per_stream(fps, p->T, p->gamma);
+    return COVA_OK;
+}
+
+static int set_batch_shape(cova_pipeline *p, uint32_t n_streams, uint32_t fps) {
+    if (!n_streams || n_streams > p->max_streams || fps > p->max_fps)
+        return set_err(COVA_E_INVAL, "batch exceeds max_streams / max_frames_per_stream of the pipeline");
+    const uint32_t wps = windows_per_stream(fps, p->T, p->gamma);
+    if (n_streams * wps > p->max_windows) return set_err(COVA_E_INVAL, "batch produces more windows than the pipeline was sized for");
+    p->cur_streams = n_streams; p->cur_fps = fps; p->cur_windows = n_streams * wps;
+    if (p->table_streams != n_streams || p->table_fps != fps) {
+        std::vector<int> newest(std::max<size_t>(1, p->cur_windows));
+        size_t k = 0;
+        for (uint32_t s = 0; s < n_streams; s++)
+            for (uint32_t w = 0; w < wps; w++) newest[k++] = (int)(s * fps + (p->T - 1) + w * p->gamma);
+        if (p->cur_windows)
+            COVA_CUDA(cudaMemcpyAsync(p->d_newest, newest.data(), sizeof(int) * p->cur_windows, cudaMemcpyHostToDevice, p->stream));
+        COVA_CUDA(cudaStreamSynchronize(p->stream));   // `newest` is a stack temporary
+        p->table_streams = n_streams; p->table_fps = fps;
+    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_load_frames(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, int is_device) {
+    if (!p || !frames) return set_err(COVA_E_INVAL, "null argument");
+    COVA_CUDA(cudaSetDevice(p->device));
+    int rc = set_batch_shape(p, n_streams, fps);
+    if (rc) return rc;
+    COVA_CUDA(cudaMemcpyAsync(p->d_frames, frames, p->frame_bytes * n_streams * fps,
+                              is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, uint32_t n, int is_device) {
+    if (!p || !masks) return set_err(COVA_E_INVAL, "null argument");
+    if (!n || n > p->max_windows) return set_err(COVA_E_INVAL, "mask batch exceeds the pipeline's window capacity");
+    COVA_CUDA(cudaSetDevice(p->device));
+    p->cur_windows = n;
+    COVA_CUDA(cudaMemcpyAsync(p->d_mask, masks, (size_t)n * p->W * p->H, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_tensorise(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    if (!p->cur_windows) return COVA_OK;
+    COVA_CUDA(cudaSetDevice(p->device));
+    const int N = (int)p->cur_windows;
+    if (p->d_stacked) {
+        const size_t S = p->frame_bytes;
+        if (S % 16 == 0) {
+            long long total = (long long)N * p->T * (S / 16);
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            stack_rgba_kernel<uint4><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint4 *>(p->d_frames), p->d_newest,
+                                                                   reinterpret_cast<uint4 *>(p->d_stacked), (int)(S / 16), (int)p->T, total);
+        } else {
+            long long total = (long long)N * p->T * (S / 4);
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            stack_rgba_kernel<uint32_t><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(p->d_frames), p->d_newest,
+                                                                      reinterpret_cast<uint32_t *>(p->d_stacked), (int)(S / 4), (int)p->T, total);
+        }
+        COVA_CUDA(cudaGetLastError());
+        p->launches++;
+        prof_mark(p, "stack_rgba");
+    }
+    long long total = (long long)N * p->H * p->gx[0].Wh * kT;
+    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
+    tensorise_x0_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(p->d_frames), p->d_newest, p->x[0], p->gx[0], N);
+    COVA_CUDA(cudaGetLastError());
+    p->launches++;
+    prof_mark(p, "tensorise_x0");
+    return COVA_OK;
+}
+
+// ---- layer launchers -------------------------------------------------------------------------------
+static void crop_for(int in_extent, int target, int &crop_lo) {
+    int pad = (2 * in_extent + 2) - target;     // decoder.py:42-59: (pad//2 + pad%2, pad//2)
+    crop_lo = pad / 2 + pad % 2;
+}
+
+static int simt_layer(cova_pipeline *p, int layer) {
+    const int N = (int)p->cur_windows;
+    const float *w = p->d_wraw;
+    if (layer < 4) {
+        const int i = layer;
+        SimtEncArgs a;
+        a.in = reinterpret_cast<const Row8 *>(p->x[i]); a.gin = p->gx[i];
+        a.out = i < 3 ? reinterpret_cast<Row8 *>(p->x[i + 1]) : nullptr;
+        a.gout = i < 3 ? p->gx[i + 1] : p->gx[3];
+        // skip of enc(i+1) feeds dec(3-i): enc1 -> D3in, enc2 -> D2in, enc3 -> D1in, enc4 -> D0in (whole input)
+        a.out2 = reinterpret_cast<Row8 *>(p->d[3 - i]); a.gout2 = p->gd[3 - i];
+        a.out2_cb = i < 3 ? kDecCout[2 - i] / 8 : 0;
+        a.w = w + p->hw.off_enc[i][0]; a.b = w + p->hw.off_enc[i][1]; a.gamma = w + p->hw.off_enc[i][2];
+        a.beta = w + p->hw.off_enc[i][3]; a.mean = w + p->hw.off_enc[i][4]; a.var = w + p->hw.off_enc[i][5];
+        a.w1 = w + p->hw.off_enc[i][6]; a.w2 = w + p->hw.off_enc[i][7];
+        a.Cin = kEncCin[i]; a.Cout = kEncCout[i]; a.N = N;
+        a.in_scale = i == 0 ? 1.0f / 6.0f : 1.0f;
+        long long total = (long long)N * (a.gin.H / 2) * (a.gin.W / 2) * (a.Cout / 8);
+        simt_encoder_kernel<<<(unsigned)((total + 127) / 128), 128, 0, p->stream>>>(a);
+        COVA_CUDA(cudaGetLastError());
+        p->launches++;
+        prof_mark(p, i == 0 ? "simt_enc1" : i == 1 ? "simt_enc2" : i == 2 ? "simt_enc3" : "simt_enc4");
+        return COVA_OK;
+    }
+    const int i = layer - 4;
+    SimtDecArgs a;
+    a.in = reinterpret_cast<const Row8 *>(p->d[i]); a.gin = p->gd[i];
+    a.out = i < 3 ? reinterpret_cast<Row8 *>(p->d[i + 1]) : nullptr;
+    a.gout = i < 3 ? p->gd[i + 1] : p->gd[3];
+    a.w = w + p->hw.off_dec[i][0]; a.b = w + p->hw.off_dec[i][1];
+    a.gamma = w + p->hw.off_dec[i][2]; a.beta = w + p->hw.off_dec[i][3]; a.mean = w + p->hw.off_dec[i][4]; a.var = w + p->hw.off_dec[i][5];
+    a.head_w = w + p->hw.off_head[0]; a.head_b = w + p->hw.off_head[1];
+    a.mask = p->d_mask; a.logits = p->d_logits;
+    a.Cin = kDecCin[i]; a.Cout = kDecCout[i]; a.N = N;
+    a.Ht = p->sizes_h[3 - i]; a.Wt = p->sizes_w[3 - i];
+    crop_for(a.gin.H, a.Ht, a.crop_t);
+    crop_for(a.gin.W, a.Wt, a.crop_l);
+    if (i < 3) {
+        long long total = (long long)N * a.Ht * a.Wt * (a.Cout / 8);
+        simt_decoder_kernel<<<(unsigned)((total + 127) / 128), 128, 0, p->stream>>>(a);
+    } else {
+        long long total = (long long)N * a.Ht * a.Wt;
+        simt_head_kernel<<<(unsigned)((total + 127) / 128), 128, 0, p->stream>>>(a);
+    }
+    COVA_CUDA(cudaGetLastError());
+    p->launches++;
+    prof_mark(p, i == 0 ? "simt_dec0" : i == 1 ? "simt_dec1" : i == 2 ? "simt_dec2" : "simt_dec3_head");
+    return COVA_OK;
+}
+
+template <class C0, class... Cs>
+static int launch_first_fit(const tc::LayerParams &lp, int n_sms, cudaStream_t st) {
+    cudaError_t err = cudaSuccess;
+    if (tc::try_launch<C0>(lp, n_sms, st, err)) {
+        if (err != cudaSuccess) return set_err(COVA_E_CUDA, "tcgen05 layer launch: %s", cudaGetErrorString(err));
+        return COVA_OK;
+    }
+    if constexpr (sizeof...(Cs) > 0) return launch_first_fit<Cs...>(lp, n_sms, st);
+    else return set_err(COVA_E_UNSUPPORTED, "no tcgen05 tile configuration fits shared memory for this macroblock grid");
+}
+
+static int tc_layer(cova_pipeline *p, int layer) {
+    using namespace tc;
+    const int N = (int)p->cur_windows;
+    LayerParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.N = N; lp.watchdog = p->d_watchdog;
+    int rc;
+    if (layer < 4) {
+        const int i = layer;
+        lp.in = p->x[i]; lp.gin = p->gx[i];
+        lp.out = i < 3 ? p->x[i + 1] : nullptr;
+        lp.gout = i < 3 ? p->gx[i + 1] : p->gx[3];
+        lp.out2 = p->d[3 - i]; lp.gout2 = p->gd[3 - i];
+        lp.out2_cb = i < 3 ? kDecCout[2 - i] / 8 : 0;
+        lp.wpack = p->enc[i].wpack; lp.epi = p->enc[i].epi;
+        memcpy(lp.tn_w1, p->hw.enc[i].tn_w1, 64);
+        memcpy(lp.tn_w2, p->hw.enc[i].tn_w2, 64);
+        lp.nsplit = 1;
+        //                                  MODE   CIN_CB NCOLS TPS KCH COUT
+        if (i == 0) rc = launch_first_fit<Cfg<MODE_ENC, 1, 16, 4, 1, 16>, Cfg<MODE_ENC, 1, 16, 2, 1, 16>, Cfg<MODE_ENC, 1, 16, 1, 1, 16>>(lp, p->n_sms, p->stream);
+        else if (i == 1) rc = launch_first_fit<Cfg<MODE_ENC, 2, 32, 4, 2, 32>, Cfg<MODE_ENC, 2, 32, 2, 2, 32>, Cfg<MODE_ENC, 2, 32, 1, 2, 32>>(lp, p->n_sms, p->stream);
+        else if (i == 2) rc = launch_first_fit<Cfg<MODE_ENC, 4, 64, 2, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 2, 64>>(lp, p->n_sms, p->stream);
+        else rc = launch_first_fit<Cfg<MODE_ENC, 8, 128, 1, 2, 128>>(lp, p->n_sms, p->stream);
+        if (rc) return rc;
+        p->launches++;
+        prof_mark(p, i == 0 ? "tc_enc1" : i == 1 ? "tc_enc2" : i == 2 ? "tc_enc3" : "tc_enc4");
+        return COVA_OK;
+    }
+    const int i = layer - 4;
+    lp.in = p->d[i]; lp.gin = p->gd[i];
+    lp.out = i < 3 ? p->d[i + 1] : nullptr;
+    lp.gout = i < 3 ? p->gd[i + 1] : p->gd[3];
+    lp.wpack = p->dec[i].wpack; lp.epi = p->dec[i].epi;
+    lp.nsplit = i == 0 ? 2 : 1;
+    lp.Ht = p->sizes_h[3 - i]; lp.Wt = p->sizes_w[3 - i];
+    crop_for(lp.gin.H, lp.Ht, lp.crop_t);
+    crop_for(lp.gin.W, lp.Wt, lp.crop_l);
+    lp.mask = p->d_mask; lp.logits = p->d_logits;
+    if (i == 0) rc = launch_first_fit<Cfg<MODE_DEC, 16, 128, 1, 2, 64>>(lp, p->n_sms, p->stream);
+    else if (i == 1) rc = launch_first_fit<Cfg<MODE_DEC, 16, 128, 1, 2, 32>>(lp, p->n_sms, p->stream);
+    else if (i == 2) rc = launch_first_fit<Cfg<MODE_DEC, 8, 64, 1, 4, 16>, Cfg<MODE_DEC, 8, 64, 1, 2, 16>>(lp, p->n_sms, p->stream);
+    else rc = launch_first_fit<Cfg<MODE_HEAD, 4, 16, 2, 4, 16>, Cfg<MODE_HEAD, 4, 16, 1, 4, 16>, Cfg<MODE_HEAD, 4, 16, 1, 2, 16>>(lp, p->n_sms, p->stream);
+    if (rc) return rc;
+    p->launches++;
+    prof_mark(p, i == 0 ? "tc_dec0" : i == 1 ? "tc_dec1" : i == 2 ? "tc_dec2" : "tc_dec3_head");
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_run_layer(cova_pipeline *p, int layer, uint32_t impl) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    if (layer < 0 || layer > 7 || impl > COVA_IMPL_SIMT) return set_err(COVA_E_INVAL, "layer must be 0..7, impl 0 or 1");
+    if (!p->cur_windows) return COVA_OK;
+    COVA_CUDA(cudaSetDevice(p->device));
+    return impl == COVA_IMPL_SIMT ? simt_layer(p, layer) : tc_layer(p, layer);
+}
+
+extern "C" int cova_pipeline_blobnet(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    if (!p->cur_windows) return COVA_OK;
+    COVA_CUDA(cudaSetDevice(p->device));
+    for (int layer = 0; layer < 8; layer++) {
+        int rc = p->impl == COVA_IMPL_SIMT ? simt_layer(p, layer) : tc_layer(p, layer);
+        if (rc) return rc;
+    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_ccl(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    COVA_CUDA(cudaSetDevice(p->device));
+    if (!p->cur_windows) {
+        COVA_CUDA(cudaMemsetAsync(p->ccl.d_cursor, 0, 2 * sizeof(unsigned long long), p->stream));
+        return COVA_OK;
+    }
+    int rc = ccl_launch(p->ccl, p->d_mask, (int)p->cur_windows, p->cc_threshold, false, p->stream);
+    if (rc) return rc;
+    p->launches++;
+    prof_mark(p, "ccl_bbox");
+    return COVA_OK;
+}
+
+static void prof_begin(cova_pipeline *p) {
+    if (!p->profiling) return;
+    p->ev_used = 0;
+    p->names.clear();
+    prof_mark(p, "start");
+}
+
+extern "C" int cova_pipeline_run(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    prof_begin(p);
+    int rc = cova_pipeline_tensorise(p);
+    if (!rc) rc = cova_pipeline_blobnet(p);
+    if (!rc) rc = cova_pipeline_ccl(p);
+    return rc;
+}
+
+extern "C" int cova_pipeline_sync(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    COVA_CUDA(cudaSetDevice(p->device));
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    if (e != cudaSuccess) {
+        unsigned int code = 0;
+        cudaMemcpy(&code, p->d_watchdog, sizeof(code), cudaMemcpyDeviceToHost);
+        char extra[64];
+        snprintf(extra, sizeof(extra), " (barrier watchdog code %u)", code);
+        return set_err(COVA_E_CUDA, "stream synchronize: %s%s", cudaGetErrorString(e), extra);
+    }
+    if (p->profiling && p->ev_used > 1) {
+        p->last_ms.clear();
+        p->last_names.clear();
+        for (size_t i = 1; i < p->ev_used; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, p->events[i - 1], p->events[i]);
+            p->last_ms.push_back(ms);
+            p->last_names.push_back(p->names[i]);
+        }
+        p->ev_used = 0;
+        p->names.clear();
+    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_fetch_boxes(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens) {
+    if (!p || !blob_len) return set_err(COVA_E_INVAL, "null argument");
+    COVA_CUDA(cudaSetDevice(p->device));
+    const size_t n = p->cur_windows;
+    unsigned long long *hp = p->h_pinned;
+    COVA_CUDA(cudaMemcpyAsync(hp, p->ccl.d_cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    if (n) {
+        COVA_CUDA(cudaMemcpyAsync(hp + 2, p->ccl.d_offsets, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+        COVA_CUDA(cudaMemcpyAsync(hp + 2 + n, p->ccl.d_lens, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    }
+    int rc = cova_pipeline_sync(p);
+    if (rc) return rc;
+    if (hp[1]) return set_err(COVA_E_CUDA, "device box arena overflow (internal sizing error)");
+    *blob_len = (size_t)hp[0];
+    if (offsets) memcpy(offsets, hp + 2, n * sizeof(uint64_t));
+    if (lens) memcpy(lens, hp + 2 + n, n * sizeof(uint64_t));
+    if (!blob || blob_cap < hp[0]) return set_err(COVA_E_TOOSMALL, "box blob needs a larger buffer");
+    if (hp[0]) {
+        COVA_CUDA(cudaMemcpyAsync(blob, p->ccl.d_blob, (size_t)hp[0], cudaMemcpyDeviceToHost, p->stream));
+        COVA_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, uint8_t *blob,
+                                          size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens, uint32_t *n_windows) {
+    int rc = cova_pipeline_load_frames(p, frames, n_streams, fps, 0);
+    if (!rc) rc = cova_pipeline_run(p);
+    if (!rc) rc = cova_pipeline_fetch_boxes(p, blob, blob_cap, blob_len, offsets, lens);
+    if (!rc && n_windows) *n_windows = p->cur_windows;
+    return rc;
+}
+
+// ---- inspection ------------------------------------------------------------------------------------
+extern "C" int cova_pipeline_read_stacked(cova_pipeline *p, uint8_t *out, size_t cap) {
+    if (!p || !out) return set_err(COVA_E_INVAL, "null argument");
+    if (!p->d_stacked) return set_err(COVA_E_INVAL, "pipeline was created without COVA_FLAG_KEEP_STACKED");
+    size_t bytes = p->frame_bytes * p->T * p->cur_windows;
+    if (cap < bytes) return set_err(COVA_E_TOOSMALL, "buffer too small");
+    int rc = cova_pipeline_sync(p);
+    if (rc) return rc;
+    COVA_CUDA(cudaMemcpy(out, p->d_stacked, bytes, cudaMemcpyDeviceToHost));
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_read_mask(cova_pipeline *p, uint8_t *out, size_t cap) {
+    if (!p || !out) return set_err(COVA_E_INVAL, "null argument");
+    size_t bytes = (size_t)p->cur_windows * p->W * p->H;
+    if (cap < bytes) return set_err(COVA_E_TOOSMALL, "buffer too small");
+    int rc = cova_pipeline_sync(p);
+    if (rc) return rc;
+    COVA_CUDA(cudaMemcpy(out, p->d_mask, bytes, cudaMemcpyDeviceToHost));
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_read_logits(cova_pipeline *p, float *out, size_t cap_floats) {
+    if (!p || !out) return set_err(COVA_E_INVAL, "null argument");
+    if (!p->d_logits) return set_err(COVA_E_INVAL, "pipeline was created without COVA_FLAG_KEEP_LOGITS");
+    size_t n = (size_t)p->cur_windows * p->W * p->H;
+    if (cap_floats < n) return set_err(COVA_E_TOOSMALL, "buffer too small");
+    int rc = cova_pipeline_sync(p);
+    if (rc) return rc;
+    COVA_CUDA(cudaMemcpy(out, p->d_logits, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_read_activation(cova_pipeline *p, int layer, float *out, size_t cap_floats, uint32_t shape[5]) {
+    if (!p || !out || !shape) return set_err(COVA_E_INVAL, "null argument");
+    if (layer < 0 || layer > 7) return set_err(COVA_E_INVAL, "layer must be 0..7");
+    const bool enc_side = layer <= 3;
+    const Geom &g = enc_side ? p->gx[layer] : p->gd[layer - 4];
+    const uint4 *src = enc_side ? p->x[layer] : p->d[layer - 4];
+    const int C = layer == 0 ? 3 : (enc_side ? kEncCout[layer - 1] : kDecCin[layer - 4]);
+    const int N = (int)p->cur_windows, Tn = g.Tn;
+    shape[0] = N; shape[1] = C; shape[2] = Tn; shape[3] = g.H; shape[4] = g.W;
+    size_t n = (size_t)N * C * Tn * g.H * g.W;
+    if (cap_floats < n) return set_err(COVA_E_TOOSMALL, "buffer too small");
+    int rc = cova_pipeline_sync(p);
+    if (rc) return rc;
+    std::vector<Row8> host((size_t)geom_rows(g));
+    COVA_CUDA(cudaMemcpy(host.data(), src, host.size() * sizeof(Row8), cudaMemcpyDeviceToHost));
+    for (int nn = 0; nn < N; nn++)
+        for (int c = 0; c < C; c++)
+            for (int t = 0; t < Tn; t++)
+                for (int y = 0; y < g.H; y++)
+                    for (int x = 0; x < g.W; x++) {
+                        const Row8 &r = host[(size_t)geom_row_of(g, nn, t, c >> 3, y, x)];
+                        out[((((size_t)nn * C + c) * Tn + t) * g.H + y) * g.W + x] = __half2float(r.v[c & 7]);
+                    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count) {
+    if (!p || !count) return set_err(COVA_E_INVAL, "null argument");
+    *count = p->launches;
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_set_profiling(cova_pipeline *p, int enable) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    p->profiling = enable != 0;
+    p->ev_used = 0;
+    p->names.clear();
+    return COVA_OK;
+}
+extern "C" int cova_pipeline_last_timings(cova_pipeline *p, char *names, size_t names_cap, float *ms, uint32_t *n) {
+    if (!p || !n) return set_err(COVA_E_INVAL, "null argument");
+    uint32_t cap = *n;
+    *n = (uint32_t)p->last_ms.size();
+    std::string joined;
+    for (size_t i = 0; i < p->last_names.size(); i++) { if (i) joined += ";"; joined += p->last_names[i]; }
+    if (names && names_cap) { strncpy(names, joined.c_str(), names_cap - 1); names[names_cap - 1] = 0; }
+    if (ms) for (uint32_t i = 0; i < std::min<uint32_t>(cap, *n); i++) ms[i] = p->last_ms[i];
+    return COVA_OK;
+}

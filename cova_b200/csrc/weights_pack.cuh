@@ -1,0 +1,177 @@
+// Host-side parsing of the CVBN v1 weight container and packing into the operand layouts the
+// kernels consume.  Container layout: see cova_b200/weights.py (torch tensor layouts, fp32).
+//
+// What is folded here, in fp32, before the one rounding to fp16:
+//   * preprocessing 1/6 (reference utils/model/preprocessing.py:5-8) into the first conv's weights
+//     (the kernel feeds the clipped integers 0..6, which are exact in fp16);
+//   * BatchNorm (eps 1e-3) into a per-channel scale/shift applied in the epilogues (it sits AFTER the
+//     ReLU and BEFORE the max-pool in the encoder - reference encoder.py:63-66 - so it cannot be folded
+//     into the conv weights there; in the decoder it directly follows the bias and is folded);
+//   * the 1x1 head conv (reference decoder.py:118,131) into the last transposed conv: no
+//     non-linearity sits between them, so dec3 + head is a transposed conv with ONE output channel.
+#pragma once
+#include "common.cuh"
+
+namespace cova {
+
+struct HostWeights {
+    struct Enc { const float *conv_w, *conv_b, *gamma, *beta, *mean, *var, *tn_w1, *tn_w2; } enc[4];
+    struct Dec { const float *convt_w, *convt_b, *gamma, *beta, *mean, *var; } dec[4];
+    const float *head_w, *head_b;
+    std::vector<float> storage;
+    size_t off_enc[4][8], off_dec[4][6], off_head[2];   // float offsets into storage (mirrored on device)
+};
+
+inline int parse_weights(const void *blob, size_t len, HostWeights &hw) {
+    if (!blob || len < 16) return set_err(COVA_E_WEIGHTS, "weight blob too short");
+    const uint32_t *h = static_cast<const uint32_t *>(blob);
+    if (h[0] != 0x4E425643u || h[1] != 1u || h[2] != (uint32_t)kT)
+        return set_err(COVA_E_WEIGHTS, "not a CVBN v1 container (magic/version/timestep)");
+    size_t need = 0;
+    for (int i = 0; i < 4; i++) need += (size_t)kEncCout[i] * kEncCin[i] * 9 + 5 * (size_t)kEncCout[i] + 32;
+    for (int i = 0; i < 4; i++) need += (size_t)kDecCin[i] * kDecCout[i] * 16 + (size_t)kDecCout[i] * (i < 3 ? 5 : 1);
+    need += kDecCout[3] + 1;
+    if (len != 16 + need * 4) return set_err(COVA_E_WEIGHTS, "CVBN container has the wrong length");
+    hw.storage.resize(need);
+    memset(hw.off_enc, 0, sizeof(hw.off_enc)); memset(hw.off_dec, 0, sizeof(hw.off_dec));
+    memcpy(hw.storage.data(), static_cast<const char *>(blob) + 16, need * 4);
+    size_t o = 0;
+    auto take = [&](size_t n, size_t &slot) { slot = o; o += n; return hw.storage.data() + slot; };
+    for (int i = 0; i < 4; i++) {
+        size_t co = kEncCout[i], ci = kEncCin[i];
+        hw.enc[i].conv_w = take(co * ci * 9, hw.off_enc[i][0]);
+        hw.enc[i].conv_b = take(co, hw.off_enc[i][1]);
+        hw.enc[i].gamma = take(co, hw.off_enc[i][2]);
+        hw.enc[i].beta = take(co, hw.off_enc[i][3]);
+        hw.enc[i].mean = take(co, hw.off_enc[i][4]);
+        hw.enc[i].var = take(co, hw.off_enc[i][5]);
+        hw.enc[i].tn_w1 = take(16, hw.off_enc[i][6]);
+        hw.enc[i].tn_w2 = take(16, hw.off_enc[i][7]);
+    }
+    for (int i = 0; i < 4; i++) {
+        size_t co = kDecCout[i], ci = kDecCin[i];
+        hw.dec[i].convt_w = take(ci * co * 16, hw.off_dec[i][0]);
+        hw.dec[i].convt_b = take(co, hw.off_dec[i][1]);
+        if (i < 3) {
+            hw.dec[i].gamma = take(co, hw.off_dec[i][2]);
+            hw.dec[i].beta = take(co, hw.off_dec[i][3]);
+            hw.dec[i].mean = take(co, hw.off_dec[i][4]);
+            hw.dec[i].var = take(co, hw.off_dec[i][5]);
+        } else {
+            hw.dec[i].gamma = hw.dec[i].beta = hw.dec[i].mean = hw.dec[i].var = nullptr;
+        }
+    }
+    hw.head_w = take(kDecCout[3], hw.off_head[0]);
+    hw.head_b = take(1, hw.off_head[1]);
+    for (float v : hw.storage)
+        if (!(v == v) || v > 3e38f || v < -3e38f) return set_err(COVA_E_WEIGHTS, "CVBN container holds NaN/Inf");
+    return COVA_OK;
+}
+
+inline int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// ---- B-operand blocks: one block = N rows x 16 K, canonical K-major no-swizzle core matrices:
+//      half index of (n, k) inside a block = ((k >> 3) * N + n) * 8 + (k & 7)
+inline void put_b(std::vector<__half> &dst, size_t block, int N, int n, int k, float v) {
+    dst[block * (size_t)N * 16 + ((size_t)(k >> 3) * N + n) * 8 + (k & 7)] = __float2half_rn(v);
+}
+
+// enc1 (3 input channels padded to one 8-channel row): 5 MMA steps per output phase, each K=16 made of
+// two taps whose operand rows sit a constant distance apart (that distance is the descriptor's LBO).
+// Both the packer and the kernel (blobnet_tc.cuh) use this table.
+struct Enc1Step { int dy0, dx0, dy1, dx1; };   // tap of K half 0 / K half 1; dy1 == 9 -> half 1 unused
+__host__ __device__ inline Enc1Step enc1_step(int a, int j) {
+    if (j < 3) return Enc1Step{j - 1, -1, j - 1, +1};
+    if (j == 3) return a == 0 ? Enc1Step{0, 0, -1, 0} : Enc1Step{-1, 0, 0, 0};
+    return Enc1Step{1, 0, 9, 9};
+}
+
+struct PackedLayer {
+    std::vector<__half> b;     // B blocks
+    std::vector<float> epi;    // epilogue constants
+    int n_cols = 0;            // N of one MMA
+    int blocks = 0;
+};
+
+// Encoder layer i: blocks indexed [tap][kpair] (i >= 1) or [phase][step] (i == 0); epi = bias|scale|shift
+inline void pack_encoder(const HostWeights &hw, int i, PackedLayer &pl) {
+    const int ci_n = kEncCin[i], co_n = kEncCout[i];
+    const auto &e = hw.enc[i];
+    auto W = [&](int co, int ci, int dy, int dx) { return e.conv_w[((size_t)(co * ci_n + ci) * 3 + (dy + 1)) * 3 + (dx + 1)]; };
+    pl.n_cols = co_n;
+    if (i == 0) {
+        pl.blocks = 4 * 5;
+        pl.b.assign((size_t)pl.blocks * co_n * 16, __float2half_rn(0.f));
+        for (int ph = 0; ph < 4; ph++)
+            for (int j = 0; j < 5; j++) {
+                Enc1Step s = enc1_step(ph >> 1, j);
+                for (int co = 0; co < co_n; co++)
+                    for (int ci = 0; ci < ci_n; ci++) {
+                        put_b(pl.b, ph * 5 + j, co_n, co, ci, W(co, ci, s.dy0, s.dx0) / 6.0f);
+                        if (s.dy1 != 9) put_b(pl.b, ph * 5 + j, co_n, co, 8 + ci, W(co, ci, s.dy1, s.dx1) / 6.0f);
+                    }
+            }
+    } else {
+        const int kp_n = ci_n / 16;
+        pl.blocks = 9 * kp_n;
+        pl.b.assign((size_t)pl.blocks * co_n * 16, __float2half_rn(0.f));
+        for (int tp = 0; tp < 9; tp++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int co = 0; co < co_n; co++)
+                    for (int k = 0; k < 16; k++)
+                        put_b(pl.b, tp * kp_n + kp, co_n, co, k, W(co, kp * 16 + k, tp / 3 - 1, tp % 3 - 1));
+    }
+    pl.epi.resize(3 * co_n);
+    for (int co = 0; co < co_n; co++) {
+        float s = e.gamma[co] / sqrtf(e.var[co] + kBnEps);
+        pl.epi[co] = e.conv_b[co];
+        pl.epi[co_n + co] = s;
+        pl.epi[2 * co_n + co] = e.beta[co] - e.mean[co] * s;
+    }
+}
+
+// Decoder layer i (< 3), N-half `half` of `nsplit`: N = (4/nsplit) parities x Cout; blocks [tap][kpair];
+// epi = scale|offset (per Cout).  Layer 3 (+ head): N = 16 (4 parities used); epi[0] = constant term.
+inline void pack_decoder(const HostWeights &hw, int i, int nsplit, int half, PackedLayer &pl) {
+    const int ci_n = kDecCin[i], co_n = kDecCout[i], kp_n = ci_n / 16;
+    const auto &d = hw.dec[i];
+    auto W = [&](int ci, int co, int ky, int kx) { return d.convt_w[((size_t)(ci * co_n + co) * 4 + ky) * 4 + kx]; };
+    pl.blocks = 4 * kp_n;
+    if (i < 3) {
+        const int par_n = 4 / nsplit;
+        pl.n_cols = par_n * co_n;
+        pl.b.assign((size_t)pl.blocks * pl.n_cols * 16, __float2half_rn(0.f));
+        for (int tp = 0; tp < 4; tp++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int pl_i = 0; pl_i < par_n; pl_i++) {
+                    int par = half * par_n + pl_i, py = par >> 1, px = par & 1, a = tp >> 1, b = tp & 1;
+                    for (int co = 0; co < co_n; co++)
+                        for (int k = 0; k < 16; k++)
+                            put_b(pl.b, tp * kp_n + kp, pl.n_cols, pl_i * co_n + co, k, W(kp * 16 + k, co, py + 2 * a, px + 2 * b));
+                }
+        pl.epi.resize(2 * co_n);
+        for (int co = 0; co < co_n; co++) {
+            float s = d.gamma[co] / sqrtf(d.var[co] + kBnEps);
+            pl.epi[co] = s;
+            pl.epi[co_n + co] = (d.convt_b[co] - d.mean[co]) * s + d.beta[co];
+        }
+    } else {
+        pl.n_cols = 16;
+        pl.b.assign((size_t)pl.blocks * 16 * 16, __float2half_rn(0.f));
+        for (int tp = 0; tp < 4; tp++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int par = 0; par < 4; par++) {
+                    int py = par >> 1, px = par & 1, a = tp >> 1, b = tp & 1;
+                    for (int k = 0; k < 16; k++) {
+                        double acc = 0;
+                        for (int co = 0; co < co_n; co++) acc += (double)W(kp * 16 + k, co, py + 2 * a, px + 2 * b) * hw.head_w[co];
+                        put_b(pl.b, tp * kp_n + kp, 16, par, k, (float)acc);
+                    }
+                }
+        double c0 = hw.head_b[0];
+        for (int co = 0; co < co_n; co++) c0 += (double)hw.head_w[co] * d.convt_b[co];
+        pl.epi.assign(4, (float)c0);
+    }
+}
+
+}  // namespace cova

@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's element interface for the blob-detection path.
+
+The reference host language is Rust (GStreamer elements in cova-rs/gst-plugins); there is no Rust
+toolchain in this image, so the layer above the C ABI is Python, keeping the reference's element names,
+property names, caps arithmetic and flow results:
+
+  MetaPreprocess   <- cova-rs/gst-plugins/src/metapreprocess/imp.rs  (properties timestep, gamma)
+  BboxCc           <- cova-rs/gst-plugins/src/bboxcc/imp.rs          (property cc-threshold, default 30)
+  BlobPipeline     <- the chain metapreprocess ! nvvideoconvert ! nvstreammux ! nvinfer(BlobNet) !
+                      nvstreamdemux ! maskcopy ! bboxcc of pipeline/cova/pipeline.py:101-250, batched
+                      over many chains, with only the bincode boxes returning to the host.
+
+All compute happens in libcova_b200.so (CUDA, sm_100a); nothing here has a CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+
+import numpy as np
+
+from . import _lib
+from ._lib import CovaError, check
+
+FLOW_OK = _lib.OK
+FLOW_DROPPED = _lib.DROPPED          # gst_base::BASE_TRANSFORM_FLOW_DROPPED
+DEFAULT_TIMESTEP = 1                 # metapreprocess/imp.rs:20
+DEFAULT_GAMMA = 1                    # metapreprocess/imp.rs:21
+DEFAULT_CC_THRESHOLD = 30            # bboxcc/imp.rs:16
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class MetaPreprocess:
+    """`metapreprocess` element: one instance == one stream == one sliding window."""
+
+    ELEMENT_NAME = "metapreprocess"
+
+    def __init__(self, width: int, height: int, timestep: int = DEFAULT_TIMESTEP, gamma: int = DEFAULT_GAMMA,
+                 device: int = 0):
+        self._h = ctypes.c_void_p()
+        check(_lib.load().cova_metapreprocess_new(ctypes.byref(self._h), device, width, height, timestep, gamma))
+        self.timestep, self._gamma = timestep, gamma
+        w, h, sz = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t()
+        check(_lib.load().cova_metapreprocess_out_caps(self._h, ctypes.byref(w), ctypes.byref(h), ctypes.byref(sz)))
+        self.out_width, self.out_height, self.out_size = w.value, h.value, sz.value
+        self.size_per_buf = self.out_size // timestep
+
+    # GObject-style property access with the reference's property names
+    def set_property(self, name: str, value: int):
+        if name == "gamma":
+            check(_lib.load().cova_metapreprocess_set_gamma(self._h, value))
+            self._gamma = value
+        elif name == "timestep":
+            raise CovaError(_lib.E_INVAL, "timestep is only mutable in READY state: create a new element")
+        else:
+            raise KeyError(name)
+
+    def get_property(self, name: str) -> int:
+        return {"gamma": self._gamma, "timestep": self.timestep}[name]
+
+    def transform_caps(self) -> dict:
+        """src caps for I420 sink caps of this size (imp.rs:247-286)."""
+        return {"format": "RGBA", "width": self.out_width, "height": self.out_height}
+
+    def transform(self, inbuf) -> tuple[int, bytes | None]:
+        a = np.frombuffer(inbuf, dtype=np.uint8) if not isinstance(inbuf, np.ndarray) else np.ascontiguousarray(inbuf).reshape(-1)
+        out = np.empty(self.out_size, dtype=np.uint8)
+        rc = check(_lib.load().cova_metapreprocess_transform(self._h, _ptr(a), a.size, _ptr(out), out.size))
+        return (FLOW_OK, out.tobytes()) if rc == FLOW_OK else (FLOW_DROPPED, None)
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_metapreprocess_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BboxCc:
+    """`bboxcc` element: mask buffer in, bincode(Vec<Bbox>) out (in place in the reference)."""
+
+    ELEMENT_NAME = "bboxcc"
+
+    def __init__(self, width: int, height: int, cc_threshold: int = DEFAULT_CC_THRESHOLD, device: int = 0):
+        self._h = ctypes.c_void_p()
+        check(_lib.load().cova_bboxcc_new(ctypes.byref(self._h), device, width, height, cc_threshold))
+        self.width, self.height = width, height
+        self._cap = _lib.load().cova_bboxcc_max_out_size(self._h)
+
+    def set_property(self, name: str, value: int):
+        if name != "cc-threshold":
+            raise KeyError(name)
+        check(_lib.load().cova_bboxcc_set_cc_threshold(self._h, value))
+
+    def get_property(self, name: str) -> int:
+        if name != "cc-threshold":
+            raise KeyError(name)
+        v = ctypes.c_uint32()
+        check(_lib.load().cova_bboxcc_get_cc_threshold(self._h, ctypes.byref(v)))
+        return v.value
+
+    def transform_ip(self, buf) -> bytes:
+        a = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+        out = np.empty(self._cap, dtype=np.uint8)
+        n = ctypes.c_size_t()
+        check(_lib.load().cova_bboxcc_transform_ip(self._h, _ptr(a), a.size, _ptr(out), out.size, ctypes.byref(n)))
+        return out[: n.value].tobytes()
+
+    def labels(self, mask: np.ndarray):
+        """What cv::connectedComponentsWithStats returns for this mask (parity helper)."""
+        a = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        labels = np.empty(self.height * self.width, dtype=np.int32)
+        nb = ((self.height + 1) // 2) * ((self.width + 1) // 2)
+        stats = np.zeros((nb + 1, 5), dtype=np.int32)
+        n = ctypes.c_int32()
+        check(_lib.load().cova_bboxcc_labels(self._h, _ptr(a), a.size, _ptr(labels), _ptr(stats), ctypes.byref(n)))
+        return n.value, labels.reshape(self.height, self.width), stats[: n.value]
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_bboxcc_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def deserialize_vec(buf: bytes) -> list[tuple]:
+    """Bbox::deserialize_vec (cova-rs/bbox/src/bbox.rs:88-90) for boxes whose Options are all None."""
+    (n,) = struct.unpack_from("<Q", buf, 0)
+    out, off = [], 8
+    for _ in range(n):
+        left, top, w, h, area = struct.unpack_from("<5f", buf, off)
+        if buf[off + 20: off + 24] != b"\0\0\0\0":
+            raise ValueError("unexpected Some(..) in a bboxcc box")
+        out.append((left, top, w, h, area))
+        off += 24
+    if off != len(buf):
+        raise ValueError("trailing bytes after Vec<Bbox>")
+    return out
+
+
+class BlobPipeline:
+    """Fused batch path on one GPU.  `process(frames)` is the call a user makes: host frames in
+    ([n_streams, frames_per_stream, h_mb, w_mb, 4] u8), per-window bincode blobs out."""
+
+    def __init__(self, w_mb: int, h_mb: int, weights_blob: bytes, max_streams: int, max_frames_per_stream: int,
+                 timestep: int = 4, gamma: int = 1, cc_threshold: int = 1, device: int = 0,
+                 impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False):
+        self._h = ctypes.c_void_p()
+        flags = impl | (_lib.FLAG_KEEP_LOGITS if keep_logits else 0) | (_lib.FLAG_KEEP_STACKED if keep_stacked else 0)
+        self._wbuf = ctypes.create_string_buffer(weights_blob, len(weights_blob))
+        check(_lib.load().cova_pipeline_new(ctypes.byref(self._h), device, w_mb, h_mb, timestep, gamma, max_streams,
+                                            max_frames_per_stream, ctypes.cast(self._wbuf, ctypes.c_void_p),
+                                            len(weights_blob), cc_threshold, flags))
+        self.w_mb, self.h_mb, self.timestep, self.gamma = w_mb, h_mb, timestep, gamma
+        self.max_streams, self.max_fps = max_streams, max_frames_per_stream
+        self.n_windows = 0
+        self._blob = None
+
+    # ---- configuration
+    def set_property(self, name: str, value: int):
+        if name != "cc-threshold":
+            raise KeyError(name)
+        check(_lib.load().cova_pipeline_set_cc_threshold(self._h, value))
+
+    def set_stream(self, cuda_stream: int | None):
+        check(_lib.load().cova_pipeline_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def windows_for(self, n_streams: int, frames_per_stream: int) -> int:
+        n = ctypes.c_uint32()
+        check(_lib.load().cova_pipeline_n_windows(self._h, n_streams, frames_per_stream, ctypes.byref(n)))
+        return n.value
+
+    # ---- stages
+    def load_frames(self, frames, n_streams: int | None = None, frames_per_stream: int | None = None):
+        """frames: numpy u8 array (host) or an int device pointer (then the two counts are required)."""
+        if isinstance(frames, np.ndarray):
+            a = np.ascontiguousarray(frames, dtype=np.uint8)
+            n_streams, frames_per_stream = a.shape[0], a.shape[1]
+            assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
+            self._keep = a
+            check(_lib.load().cova_pipeline_load_frames(self._h, _ptr(a), n_streams, frames_per_stream, 0))
+        else:
+            check(_lib.load().cova_pipeline_load_frames(self._h, ctypes.c_void_p(int(frames)), n_streams, frames_per_stream, 1))
+        self.n_windows = self.windows_for(n_streams, frames_per_stream)
+
+    def load_masks(self, masks, n: int | None = None):
+        if isinstance(masks, np.ndarray):
+            a = np.ascontiguousarray(masks, dtype=np.uint8)
+            n = a.shape[0]
+            self._keep = a
+            check(_lib.load().cova_pipeline_load_masks(self._h, _ptr(a), n, 0))
+        else:
+            check(_lib.load().cova_pipeline_load_masks(self._h, ctypes.c_void_p(int(masks)), n, 1))
+        self.n_windows = n
+
+    def tensorise(self):
+        check(_lib.load().cova_pipeline_tensorise(self._h))
+
+    def blobnet(self):
+        check(_lib.load().cova_pipeline_blobnet(self._h))
+
+    def run_layer(self, layer: int, impl: int):
+        check(_lib.load().cova_pipeline_run_layer(self._h, layer, impl))
+
+    def ccl(self):
+        check(_lib.load().cova_pipeline_ccl(self._h))
+
+    def run(self):
+        check(_lib.load().cova_pipeline_run(self._h))
+
+    def sync(self):
+        check(_lib.load().cova_pipeline_sync(self._h))
+
+    def fetch_boxes(self) -> list[bytes]:
+        n = self.n_windows
+        cap = n * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
+        if self._blob is None or self._blob.size < cap:
+            self._blob = np.empty(max(cap, 8), dtype=np.uint8)
+        offs = np.zeros(max(n, 1), dtype=np.uint64)
+        lens = np.zeros(max(n, 1), dtype=np.uint64)
+        ln = ctypes.c_size_t()
+        check(_lib.load().cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens)))
+        self.last_blob_len = ln.value
+        return [self._blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs[:n], lens[:n])]
+
+    def process(self, frames: np.ndarray) -> list[bytes]:
+        """Host frames -> list of bincode(Vec<Bbox>) blobs, one per window (stream-major, time-minor)."""
+        self.load_frames(frames)
+        self.run()
+        return self.fetch_boxes()
+
+    # ---- inspection (parity tests)
+    def read_stacked(self) -> np.ndarray:
+        out = np.empty((self.n_windows, self.timestep * self.h_mb, self.w_mb, 4), dtype=np.uint8)
+        check(_lib.load().cova_pipeline_read_stacked(self._h, _ptr(out), out.size))
+        return out
+
+    def read_mask(self) -> np.ndarray:
+        out = np.empty((self.n_windows, self.h_mb, self.w_mb), dtype=np.uint8)
+        check(_lib.load().cova_pipeline_read_mask(self._h, _ptr(out), out.size))
+        return out
+
+    def read_logits(self) -> np.ndarray:
+        out = np.empty((self.n_windows, self.h_mb, self.w_mb), dtype=np.float32)
+        check(_lib.load().cova_pipeline_read_logits(self._h, _ptr(out), out.size))
+        return out
+
+    def read_activation(self, layer: int) -> np.ndarray:
+        cap = self.n_windows * 128 * 4 * self.h_mb * self.w_mb
+        out = np.empty(cap, dtype=np.float32)
+        shape = (ctypes.c_uint32 * 5)()
+        check(_lib.load().cova_pipeline_read_activation(self._h, layer, _ptr(out), out.size, shape))
+        shp = tuple(int(v) for v in shape)
+        return out[: int(np.prod(shp))].reshape(shp).copy()
+
+    def launch_count(self) -> int:
+        c = ctypes.c_uint64()
+        check(_lib.load().cova_pipeline_launch_count(self._h, ctypes.byref(c)))
+        return c.value
+
+    def set_profiling(self, enable: bool):
+        check(_lib.load().cova_pipeline_set_profiling(self._h, int(enable)))
+
+    def last_timings(self) -> dict[str, float]:
+        names = ctypes.create_string_buffer(1024)
+        ms = (ctypes.c_float * 64)()
+        n = ctypes.c_uint32(64)
+        check(_lib.load().cova_pipeline_last_timings(self._h, names, 1024, ms, ctypes.byref(n)))
+        keys = names.value.decode().split(";") if names.value else []
+        return {k: float(ms[i]) for i, k in enumerate(keys)}
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_pipeline_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,158 @@
+/* cova_b200 - C ABI of the B200-native blob-detection path of CoVA.
+ *
+ * Everything a Rust (cgo / JNI / ctypes ...) host needs is plain pointers and sizes; no CUDA or
+ * torch types appear in any signature.  A CUDA stream, where accepted, travels as void*.
+ *
+ * Conventions:
+ *   return 0 (COVA_OK) on success, COVA_DROPPED (1) when an element produced no output for this
+ *   input (GStreamer's BASE_TRANSFORM_FLOW_DROPPED), a negative COVA_E_* on error.  The library
+ *   never aborts across the FFI boundary; cova_last_error() gives a thread-local detail string.
+ *   Handles are single-caller (one streaming thread per element instance, as in the reference);
+ *   different handles may be used concurrently from different threads.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef COVA_B200_H
+#define COVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COVA_OK 0
+#define COVA_DROPPED 1
+#define COVA_E_INVAL (-1)       /* bad argument */
+#define COVA_E_CUDA (-2)        /* a CUDA call failed; see cova_last_error() */
+#define COVA_E_NOMEM (-3)
+#define COVA_E_TOOSMALL (-4)    /* output buffer too small; the required size is reported */
+#define COVA_E_WEIGHTS (-5)     /* not a CVBN v1 weight container */
+#define COVA_E_UNSUPPORTED (-6) /* e.g. timestep != 4 for BlobNet, grid too large for the CCL kernel */
+#define COVA_E_NODEVICE (-7)    /* no CUDA device: there is no CPU fallback */
+
+const char *cova_version(void);
+const char *cova_strerror(int code);
+const char *cova_last_error(void);
+int cova_device_count(int *n);
+
+/* ------------------------------------------------------------------------------------------------
+ * metapreprocess element   (cova-rs/gst-plugins/src/metapreprocess/imp.rs)
+ *   properties timestep, gamma            imp.rs:57-133  (u32 >= 1, defaults 1)
+ *   caps: I420 WxH -> RGBA (W/16) x (H/16*timestep), integer division   imp.rs:247-286
+ *   transform(): sliding window, first timestep-1 buffers dropped, gamma sub-sampling  imp.rs:288-332
+ * One handle == one element instance == one stream.  The window lives in device memory; the stacking
+ * is done by the tensorise kernel (csrc/tensorise.cuh).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_metapreprocess cova_metapreprocess;
+
+int cova_metapreprocess_new(cova_metapreprocess **out, int device, uint32_t width_px, uint32_t height_px,
+                            uint32_t timestep, uint32_t gamma);
+void cova_metapreprocess_free(cova_metapreprocess *mp);
+/* mutable like the GObject property (imp.rs:104-113) */
+int cova_metapreprocess_set_gamma(cova_metapreprocess *mp, uint32_t gamma);
+/* transform_caps(): output RGBA width/height and buffer size in bytes */
+int cova_metapreprocess_out_caps(const cova_metapreprocess *mp, uint32_t *width, uint32_t *height, size_t *size);
+/* transform(): reads the first size/timestep bytes of inbuf (host memory).  COVA_OK: outbuf holds the
+ * stacked RGBA image (row block k = frame t-k).  COVA_DROPPED: nothing written. */
+int cova_metapreprocess_transform(cova_metapreprocess *mp, const uint8_t *inbuf, size_t in_len, uint8_t *outbuf,
+                                  size_t out_cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * bboxcc element   (cova-rs/gst-plugins/src/bboxcc/imp.rs, process.rs)
+ *   property cc-threshold u32, default 30, mutable while PLAYING      imp.rs:16,51-101
+ *   transform_ip(): mask (height rows of len/height bytes, any non-zero byte = foreground)
+ *     -> 8-connected components (cv::connectedComponentsWithStats order) -> keep pixel-area >= threshold
+ *     -> bincode(Vec<Bbox>) replaces the buffer content                imp.rs:232-272, process.rs:5-49
+ *   wire format: u64 LE count, then per box 5 x f32 LE (left, top, width, height, width*height) and
+ *   four 0x00 Option tags = 24 bytes                                   cova-rs/bbox/src/bbox.rs:3-29,84-86
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_bboxcc cova_bboxcc;
+
+int cova_bboxcc_new(cova_bboxcc **out, int device, uint32_t width, uint32_t height, uint32_t cc_threshold);
+void cova_bboxcc_free(cova_bboxcc *cc);
+int cova_bboxcc_set_cc_threshold(cova_bboxcc *cc, uint32_t cc_threshold);
+int cova_bboxcc_get_cc_threshold(const cova_bboxcc *cc, uint32_t *cc_threshold);
+/* upper bound of the serialized size for this grid: 8 + 24*ceil(H/2)*ceil(W/2) */
+size_t cova_bboxcc_max_out_size(const cova_bboxcc *cc);
+/* COVA_E_TOOSMALL sets *out_len to the required size (the reference re-allocates, imp.rs:253-258) */
+int cova_bboxcc_transform_ip(cova_bboxcc *cc, const uint8_t *mask, size_t mask_len, uint8_t *out, size_t out_cap,
+                             size_t *out_len);
+/* parity helper: what cv::connectedComponentsWithStats returns.  labels: i32[H*W]; stats: i32[n*5]
+ * (left, top, width, height, area) with row 0 (background) zeroed; stats capacity must be
+ * (ceil(H/2)*ceil(W/2)+1)*5 ints.  *n_labels counts the background. */
+int cova_bboxcc_labels(cova_bboxcc *cc, const uint8_t *mask, size_t mask_len, int32_t *labels, int32_t *stats,
+                       int32_t *n_labels);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused batch path: tensorise -> BlobNet -> threshold -> CCL on device, boxes only come back.
+ * Replaces the chain metapreprocess -> nvvideoconvert -> nvstreammux -> nvinfer(TensorRT BlobNet)
+ * -> nvstreamdemux -> maskcopy -> bboxcc (pipeline/cova/pipeline.py:101-250), for many chains at once.
+ *
+ * A batch is n_streams independent chains of frames_per_stream consecutive frames each, every chain
+ * starting with an empty window exactly like a freshly started element (gopsplit hands every chain
+ * whole GoPs, gst-plugins/gst-gopsplit/gstgopsplit.cpp:557-630).  Windows are emitted in stream-major,
+ * time-minor order; window w of a stream is the one whose newest frame is (timestep-1) + w*gamma.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_pipeline cova_pipeline;
+
+#define COVA_IMPL_TCGEN05 0u /* product path: tcgen05/TMEM implicit GEMM */
+#define COVA_IMPL_SIMT 1u    /* validation kernels (CUDA cores, fp32 weights) used by the tests */
+#define COVA_FLAG_KEEP_LOGITS 0x100u  /* also store fp32 logits (parity tests) */
+#define COVA_FLAG_KEEP_STACKED 0x200u /* also materialise the stacked RGBA windows (parity tests) */
+
+int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb, uint32_t h_mb, uint32_t timestep,
+                      uint32_t gamma, uint32_t max_streams, uint32_t max_frames_per_stream, const void *weights,
+                      size_t weights_len, uint32_t cc_threshold, uint32_t flags);
+void cova_pipeline_free(cova_pipeline *p);
+int cova_pipeline_set_cc_threshold(cova_pipeline *p, uint32_t cc_threshold);
+/* run all kernels on this stream (a cudaStream_t / CUstream as void*); NULL = the pipeline's own */
+int cova_pipeline_set_stream(cova_pipeline *p, void *cuda_stream);
+/* number of windows a batch of this shape produces */
+int cova_pipeline_n_windows(const cova_pipeline *p, uint32_t n_streams, uint32_t frames_per_stream, uint32_t *n);
+
+/* stage 0: put a batch of frames [n_streams][frames_per_stream][h_mb][w_mb][4] into the device frame pool.
+ * is_device != 0: frames is a device pointer (device-to-device copy). Asynchronous on the stream. */
+int cova_pipeline_load_frames(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams,
+                              uint32_t frames_per_stream, int is_device);
+/* stages, each asynchronous on the stream, operating on the loaded batch */
+int cova_pipeline_tensorise(cova_pipeline *p); /* frame pool -> BlobNet input layout (+ stacked RGBA if kept) */
+int cova_pipeline_blobnet(cova_pipeline *p);   /* -> mask u8 {0,1} [n_windows][h_mb][w_mb] on device */
+int cova_pipeline_ccl(cova_pipeline *p);       /* mask -> bincode blobs + offsets on device */
+int cova_pipeline_run(cova_pipeline *p);       /* the three above */
+int cova_pipeline_sync(cova_pipeline *p);
+/* copy the boxes back: blob = concatenation of per-window bincode(Vec<Bbox>); window i occupies
+ * [offsets[i], offsets[i] + lens[i]).  offsets/lens have n_windows entries.  Synchronises. */
+int cova_pipeline_fetch_boxes(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                              uint64_t *lens);
+/* one call, host buffers in and out (the call a GStreamer element would make per batch) */
+int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams,
+                               uint32_t frames_per_stream, uint8_t *blob, size_t blob_cap, size_t *blob_len,
+                               uint64_t *offsets, uint64_t *lens, uint32_t *n_windows);
+
+/* feed a mask batch straight to the CCL stage (u8 [n][h_mb][w_mb]; is_device as above) */
+int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, uint32_t n, int is_device);
+
+/* parity / inspection (synchronise; host output buffers) */
+int cova_pipeline_read_stacked(cova_pipeline *p, uint8_t *out, size_t cap);  /* [n_windows][T*h][w][4] */
+int cova_pipeline_read_mask(cova_pipeline *p, uint8_t *out, size_t cap);     /* [n_windows][h][w] */
+int cova_pipeline_read_logits(cova_pipeline *p, float *out, size_t cap_floats); /* [n_windows][h][w] */
+/* activation `layer` (0 = BlobNet input, 1..4 = encoder outputs, 5..7 = decoder concat inputs dec1..dec3)
+ * de-permuted to float [n_windows][C][T][H][W]; dims returned in shape[5] = {N, C, T, H, W} */
+int cova_pipeline_read_activation(cova_pipeline *p, int layer, float *out, size_t cap_floats, uint32_t shape[5]);
+/* run ONE BlobNet layer (0..3 = enc1..enc4, 4..6 = dec0..dec2, 7 = dec3 + head) with the chosen
+ * implementation on whatever its input buffer currently holds - lets the tests compare the tcgen05
+ * kernel of a layer against the validation kernel of the same layer on identical inputs */
+int cova_pipeline_run_layer(cova_pipeline *p, int layer, uint32_t impl);
+/* kernels launched by this handle since creation */
+int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count);
+/* per-kernel device time of the last cova_pipeline_run* with profiling enabled: names is a
+ * ';'-separated list, ms has one entry per name.  enable != 0 records CUDA events around every kernel. */
+int cova_pipeline_set_profiling(cova_pipeline *p, int enable);
+int cova_pipeline_last_timings(cova_pipeline *p, char *names, size_t names_cap, float *ms, uint32_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVA_B200_H */

@@ -1,0 +1,94 @@
+"""CPU tests of the host logic and the C-ABI surface (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cova_b200 import _lib, shard, synth, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cova_b200.h")).read()
+    declared = set(re.findall(r"\b(cova_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cova_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.cova_version()
+
+
+def test_no_cpu_fallback_without_device():
+    lib = _lib.load()
+    n = ctypes.c_int(-1)
+    assert lib.cova_device_count(ctypes.byref(n)) == 0
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    h = ctypes.c_void_p()
+    for rc in (lib.cova_bboxcc_new(ctypes.byref(h), 0, 80, 45, 1),
+               lib.cova_metapreprocess_new(ctypes.byref(h), 0, 1280, 720, 4, 1)):
+        assert rc == _lib.E_NODEVICE and not h.value
+    blob = weights.to_blob(weights.random_weights(0))
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    rc = lib.cova_pipeline_new(ctypes.byref(h), 0, 80, 45, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1, 0)
+    assert rc == _lib.E_NODEVICE
+    assert b"no CPU fallback" in lib.cova_last_error()
+
+
+def test_argument_validation_comes_before_device_use():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.cova_metapreprocess_new(ctypes.byref(h), 0, 1280, 720, 0, 1) == _lib.E_INVAL      # timestep >= 1
+    assert lib.cova_bboxcc_new(ctypes.byref(h), 0, 0, 45, 1) == _lib.E_INVAL
+    assert lib.cova_pipeline_new(ctypes.byref(h), 0, 80, 45, 3, 1, 1, 8, None, 0, 1, 0) == _lib.E_UNSUPPORTED
+    assert lib.cova_strerror(_lib.E_TOOSMALL) == b"output buffer too small"
+
+
+def test_weight_container_roundtrip_and_size():
+    w = weights.random_weights(3)
+    blob = weights.to_blob(w)
+    assert len(blob) == 16 + 4 * weights.n_params()
+    assert 300_000 < weights.n_params() < 340_000          # "~320 K parameters"
+    w2 = weights.from_blob(blob)
+    for k in w:
+        assert (w[k] == w2[k]).all()
+    from oracle import blobnet_ref
+    w3 = blobnet_ref.parse_blob(blob)
+    assert all((w[k] == w3[k]).all() for k in w)
+    with pytest.raises(ValueError):
+        weights.from_blob(blob[:-4])
+
+
+def test_flops_per_window_match_survey():
+    from oracle import blobnet_ref
+    assert blobnet_ref.flops_per_window(45, 80) == 153_786_880
+    assert blobnet_ref.flops_per_window(68, 120) == 340_823_040
+    assert blobnet_ref.flops_per_window(135, 240) == 1_333_946_880
+
+
+def test_gopsplit_ranges_remainder_to_last_pad():
+    assert shard.gop_ranges(8, 3) == [(0, 2), (2, 4), (4, 8)]
+    assert shard.gop_ranges(7, 8)[-1] == (0, 7) and shard.gop_ranges(7, 8)[0] == (0, 0)
+    key = [i % 250 == 0 for i in range(1802)]              # demo/1m.mp4: 1802 frames, 8 key frames
+    spans = [shard.frames_of_shard(key, 4, p) for p in range(4)]
+    assert spans == [(0, 500), (500, 1000), (1000, 1500), (1500, 1802)]
+    # every chain restarts its window: 3 frames per shard emit nothing
+    assert sum(shard.windows_of_chain(e - s, 4) for s, e in spans) == 1802 - 4 * 3
+
+
+def test_stream_sharding_is_a_partition():
+    for world in (1, 2, 4, 8):
+        got = sorted(s for r in range(world) for s in shard.streams_of_rank(256, world, r))
+        assert got == list(range(256))
+
+
+def test_synthetic_stream_statistics():
+    fr = synth.synth_streams(2, 67, 45, 80, config_idx=1)
+    assert fr.shape == (2, 67, 45, 80, 4) and fr.dtype == np.uint8
+    assert (fr[:, 0, :, :, 0] == 6).all()                  # frame 0 is the IDR: all intra
+    assert fr[..., 3].max() <= 4                           # stale byte
+    assert (fr[:, 1:, :, :, 0] == 1).mean() > 0.8          # mostly skip MBs
