@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the blob-detection hot path (tensorise -> BlobNet -> CCL/bbox) on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                     # the CPU path (oracle port) on the host cores
+
+A step = one pass of the whole path over one batch: 128 independent 720p chains (80x45 macroblocks) of
+67 frames each = 64 windows per chain, 8192 windows per GPU per step (BASELINE.json configs[1] shape per
+chain, configs[4] chain count per GPU).  `value` counts detections (output windows) per second with the
+frames resident in HBM; `e2e` is the same through BlobPipeline.process() with pinned host frames in and
+bincode boxes out.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H_MB, W_MB, T = 45, 80, 4
+STREAMS_PER_GPU, FRAMES_PER_STREAM = 128, 67
+METRIC, UNIT = "blob_detection_frames_per_sec", "frames/s"
+LAYER_NAMES = ["tc_enc1", "tc_enc2", "tc_enc3", "tc_enc4", "tc_dec0", "tc_dec1", "tc_dec2", "tc_dec3_head"]
+
+
+def layer_flops(h, w):
+    """Algorithmic 2*MAC per window of every BlobNet layer kernel (PointWiseTN is
+    counted with its encoder layer, the 1x1 head with dec3)."""
+    enc_ch = [(3, 16), (16, 32), (32, 64), (64, 128)]
+    dec_ch = [(128, 64), (128, 32), (64, 16), (32, 16)]
+    out, sizes = [], []
+    hh, ww = h, w
+    for ci, co in enc_ch:
+        mac = T * hh * ww * 9 * ci * co
+        hh, ww = (hh + 1) // 2, (ww + 1) // 2
+        mac += co * hh * ww * 2 * T * T
+        sizes.append((hh, ww))
+        out.append(2 * mac)
+    for i, (ci, co) in enumerate(dec_ch):
+        mac = hh * ww * 16 * ci * co
+        hh, ww = sizes[2 - i] if i < 3 else (h, w)
+        if i == 3:
+            mac += h * w * co
+        out.append(2 * mac)
+    return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU path
+def cpu_path(frames, w, threads):
+    """The reference's CPU path restated (oracle port): metapreprocess memcpy stack -> BlobNet fp32 on a CPU
+    runtime (torch CPU stands in for ONNX, absent offline) -> threshold -> OpenCV-order CCL + bincode."""
+    import torch
+    from oracle import blobnet_ref, c_oracle, metapreprocess_ref as mpr
+    torch.set_num_threads(threads)
+    stacked = np.concatenate([c_oracle.metapreprocess_stream(frames[s], T, 1) for s in range(frames.shape[0])])
+    logits = blobnet_ref.blobnet_forward(w, mpr.stacked_to_nchw(stacked, T))
+    blobs = c_oracle.bboxcc_batch(blobnet_ref.mask_from_logits(logits), 1)
+    return len(blobs)
+
+
+def time_cpu(w, steps, warmup, target_s=4.0):
+    from cova_b200 import synth
+    threads = os.cpu_count() or 1
+    fps = FRAMES_PER_STREAM
+    probe = synth.tiled_streams(1, fps, H_MB, W_MB, 1)
+    t0 = time.perf_counter()
+    n1 = cpu_path(probe, w, threads)
+    dt = time.perf_counter() - t0
+    n_streams = int(max(1, min(16, target_s / max(dt, 1e-3))))
+    frames = synth.tiled_streams(n_streams, fps, H_MB, W_MB, 1)
+    for _ in range(max(0, warmup - 1)):
+        cpu_path(frames, w, threads)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        n += cpu_path(frames, w, threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_streams} chains x {fps} frames of 720p per step ({n // steps} windows), {steps} steps, "
+                      f"C oracle tensorise/CCL + torch-CPU fp32 BlobNet, {threads} threads"}, dt / steps * 1e3, n1
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cova_b200", choices=["cova_b200", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cova_b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from cova_b200 import weights
+    w = weights.random_weights(0, head_bias=-1.0)
+    workload = (f"synthetic 720p metadata (80x45 MB grid), {args.streams} chains x {FRAMES_PER_STREAM} frames "
+                f"(64-window batch per chain) per GPU")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 5)
+        cb, ms, _ = time_cpu(w, steps, min(args.warmup, 1))
+        cb_line = dict(cb)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "note": "CPU path = oracle port (the Rust/GStreamer/TensorRT reference cannot be built here); "
+                       "each step is a bounded sample of the workload"},
+            "cpu_baseline": cb_line,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cova_b200 has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cova_b200 import _lib, synth
+    from cova_b200.elements import BlobPipeline
+
+    n_streams, fps = args.streams, FRAMES_PER_STREAM
+    # stream-sharded: rank r owns chains r, r+world, ... of the global set (weak scaling: n_streams per GPU)
+    frames_np = synth.tiled_streams(n_streams, fps, H_MB, W_MB, config_idx=1 + rank)
+    pinned = torch.empty(frames_np.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = frames_np
+    pipe = BlobPipeline(W_MB, H_MB, weights.to_blob(w), n_streams, fps, cc_threshold=1, device=local_rank,
+                        impl=_lib.IMPL_TCGEN05)
+    # a real (non-default) stream, shared by torch's events and the library's kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    pipe.set_stream(stream.cuda_stream)
+    n_windows = pipe.windows_for(n_streams, fps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: frames already in HBM
+    dev_frames = pinned.cuda(non_blocking=False)
+    pipe.load_frames(dev_frames.data_ptr(), n_streams, fps)
+    for _ in range(args.warmup):
+        pipe.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = pipe.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        pipe.run()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pipe.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n_windows * world / (ms_step * 1e-3)
+
+    # ---- per-kernel durations, live, CUDA events on the launching stream
+    pipe.set_profiling(True)
+    acc = {}
+    for _ in range(5):
+        pipe.run()
+        pipe.sync()
+        for k, v in pipe.last_timings().items():
+            acc.setdefault(k, []).append(v)
+    pipe.set_profiling(False)
+    kms = {k: float(np.mean(v)) for k, v in acc.items()}
+
+    # ---- end to end: pinned host frames -> boxes on the host, through the public call
+    host_frames = pinned.numpy()
+    for _ in range(2):
+        pipe.process(host_frames, raw=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    d2h = 0
+    e2e_steps = max(3, args.steps // 4)
+    for _ in range(e2e_steps):
+        blob, offs, lens = pipe.process(host_frames, raw=True)
+        d2h = pipe.last_blob_len + 16 + 16 * n_windows
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    t = torch.tensor([e2e_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_windows * world / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        fl = layer_flops(H_MB, W_MB)
+        stages = {}
+        for name, f in zip(LAYER_NAMES, fl):
+            if name in kms:
+                tf = f * n_windows / (kms[name] * 1e-3) / 1e12
+                stages[name] = {"ms": round(kms[name], 4), "achieved_tflops": round(tf, 1), "frac": round(tf / pk["tflops"], 4)}
+        if "tensorise_x0" in kms:
+            gb = 20 * H_MB * W_MB * n_windows / (kms["tensorise_x0"] * 1e-3) / 1e9
+            stages["tensorise_x0"] = {"ms": round(kms["tensorise_x0"], 4), "achieved_gbs": round(gb, 1), "frac": round(gb / pk["hbm_gbs"], 4)}
+        if "ccl_bbox" in kms:
+            nbox = float(((lens.astype(np.int64) - 8) // 24).mean())
+            gb = (H_MB * W_MB + 24 * nbox + 8) * n_windows / (kms["ccl_bbox"] * 1e-3) / 1e9
+            stages["ccl_bbox"] = {"ms": round(kms["ccl_bbox"], 4), "achieved_gbs": round(gb, 1), "frac": round(gb / pk["hbm_gbs"], 5),
+                                  "boxes_per_frame": round(nbox, 2)}
+        dom = max((k for k in kms if k.startswith("tc_")), key=lambda k: kms[k])
+        roof = {"bound": "tensor", "kernel": dom, "achieved": stages[dom]["achieved_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                "frac": stages[dom]["frac"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16, kernel timed inside the step)",
+                "whole_blobnet_frac": round(sum(fl) * n_windows / (sum(kms[k] for k in LAYER_NAMES if k in kms) * 1e-3) / 1e12 / pk["tflops"], 4)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _, _ = time_cpu(w, 2, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": workload, "windows_per_gpu_per_step": n_windows, "timestep": T, "gamma": 1, "cc_threshold": 1,
+                       "l2": "per-step working set (activations ~5 GB) far exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"chain-sharded x{world}, no collective", "weights": "random-init (seed 0), reference architecture"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel()), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "roofline": roof, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

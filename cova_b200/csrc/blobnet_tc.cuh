@@ -24,7 +24,8 @@ namespace tc {
 
 constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2;
 constexpr int kMaxStage = 4;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                 // 4 groups of 4 warps (one per TMEM lane quarter)
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct LayerParams {
     const uint4 *in; Geom gin;
@@ -125,7 +126,11 @@ struct Cfg {
     static constexpr int MODE = MODE_, CIN_CB = CIN_CB_, NCOLS = NCOLS_, TPS = TPS_, KCH = KCH_, COUT = COUT_;
     static constexpr int NKC = CIN_CB / KCH;
     static constexpr int COLS_TILE = 4 * NCOLS;
-    static constexpr int NSLOT = (512 / COLS_TILE) < 4 ? (512 / COLS_TILE) : 4;
+    static constexpr int NSLOT = (512 / COLS_TILE) < 8 ? (512 / COLS_TILE) : 8;
+    // the 4 epilogue warp groups split a tile by channel group (CG) and, when a tile has fewer than 4
+    // channel blocks, also take alternate tiles (TG); decoder / head groups take one input phase each
+    static constexpr int CG = MODE_ == MODE_ENC ? ((COUT_ / 8) < 4 ? (COUT_ / 8) : 4) : 4;
+    static constexpr int TG = 4 / CG;
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * COLS_TILE);
     static constexpr bool ENC1 = (MODE == MODE_ENC && CIN_CB == 1);
     static constexpr int NTAP = MODE == MODE_ENC ? 9 : 4;
@@ -134,6 +139,7 @@ struct Cfg {
     static_assert(NKC == 1 || TPS == 1, "accumulating over k-chunks needs one tile per stage");
     static_assert(ENC1 || (KCH % 2 == 0), "a K=16 step spans two channel blocks");
     static_assert(COLS_TILE <= 512, "accumulators exceed TMEM");
+    static_assert(NSLOT >= TG, "tile-parallel epilogue groups need their own accumulator slots");
 };
 
 struct SmemPlan {
@@ -147,7 +153,7 @@ __host__ __device__ inline SmemPlan plan_smem(int Ls, int n_stage, int w_bytes, 
     s.stage_bytes = (uint32_t)(C::KCH * 4 * Ls * 16);
     s.epi_off = s.stage_off + (uint32_t)n_stage * s.stage_bytes;
     s.bar_off = s.epi_off + (uint32_t)((epi_floats * 4 + 15) / 16 * 16);
-    s.total = s.bar_off + 8 * (2 * kMaxStage + 2 * 4 + 1) + 16;
+    s.total = s.bar_off + 8 * (2 * kMaxStage + 2 * 8 + 1) + 16;
     return s;
 }
 template <class C>
@@ -218,7 +224,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 template <class C>
-__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int lane) {
+__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int lane, int cg) {
     const Geom &gi = p.gin;
     const int t = pp & 3;
     const int qq = pp >> 2;
@@ -238,8 +244,9 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
 #pragma unroll
     for (int m = 0; m < 4; m++) w2c[m] = w2s[m * 4 + t];          // column t of W2
     const int qbase = lane & ~3;
+    constexpr int CB_PER = (C::COUT / 8) / C::CG;                 // channel blocks of this warp group
 #pragma unroll 1
-    for (int cb = 0; cb < C::COUT / 8; cb++) {
+    for (int cb = cg * CB_PER; cb < (cg + 1) * CB_PER; cb++) {
         uint32_t v[4][8];
 #pragma unroll
         for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
@@ -249,9 +256,13 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
         for (int j = 0; j < 8; j++) {
             const int c = cb * 8 + j;
             const float b = bias[c], s = scale[c], sh = shift[c];
-            float m = fmaf(fmaxf(__uint_as_float(v[0][j]) + b, 0.f), s, sh);                  // ReLU -> BN
-#pragma unroll
-            for (int ph = 1; ph < 4; ph++) m = fmaxf(m, fmaf(fmaxf(__uint_as_float(v[ph][j]) + b, 0.f), s, sh));   // MaxPool
+            // MaxPool(BN(ReLU(x + b))): x -> fma(max(x + b, 0), s, sh) is monotone (non-decreasing for s >= 0,
+            // non-increasing for s < 0), so the pool maximum is attained at max(x) resp. min(x): bit-identical
+            // to pooling the four activated values, with a quarter of the arithmetic.
+            const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
+            const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
+            const float hi = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), lo = fminf(fminf(a0, a1), fminf(a2, a3));
+            const float m = fmaf(fmaxf((s >= 0.f ? hi : lo) + b, 0.f), s, sh);
             // PointWiseTN: the 4 frames of this window position are the 4 lanes of this quad
             float xs[4];
 #pragma unroll
@@ -276,68 +287,63 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
     }
 }
 
+// decoder: warp group `ph` owns the accumulator of input phase ph
 template <class C>
-__device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int half) {
+__device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int half, int ph) {
     const Geom &gi = p.gin;
     const int n = pp / gi.S;
     const int r = pp - n * gi.S;
     const int y2 = r / gi.P, x2 = r - y2 * gi.P;
     constexpr int PARN = C::NCOLS / C::COUT;   // output parities handled by this CTA
     const float *scale = epi, *offs = epi + C::COUT;
+    const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);   // position in the (Hin+1) x (Win+1) sub-pixel grid
+    const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
 #pragma unroll 1
-    for (int ph = 0; ph < 4; ph++) {
-        const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);   // position in the (Hin+1) x (Win+1) sub-pixel grid
-        const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
-#pragma unroll 1
-        for (int pl = 0; pl < PARN; pl++) {
-            const int par = half * PARN + pl;
-            const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
-            const bool valid = vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt;
-            long long row = 0;
-            if (valid) row = geom_row(p.gout, 0, ((Y & 1) << 1) | (X & 1), geom_pos(p.gout, n, Y >> 1, X >> 1, 0));
+    for (int pl = 0; pl < PARN; pl++) {
+        const int par = half * PARN + pl;
+        const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
+        const bool valid = vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt;
+        long long row = 0;
+        if (valid) row = geom_row(p.gout, 0, ((Y & 1) << 1) | (X & 1), geom_pos(p.gout, n, Y >> 1, X >> 1, 0));
 #pragma unroll
-            for (int cb = 0; cb < C::COUT / 8; cb++) {
-                uint32_t v[8];
-                tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + pl * C::COUT + cb * 8), v);
-                tmem_wait_ld();
-                if (valid) {
-                    float o[8];
+        for (int cb = 0; cb < C::COUT / 8; cb++) {
+            uint32_t v[8];
+            tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + pl * C::COUT + cb * 8), v);
+            tmem_wait_ld();
+            if (valid) {
+                float o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        o[j] = fmaxf(fmaf(__uint_as_float(v[j]), scale[cb * 8 + j], offs[cb * 8 + j]), 0.f);   // bias+BN, then the consumer's ReLU
-                    uint4 rw;
-                    rw.x = pack_half2(o[0], o[1]); rw.y = pack_half2(o[2], o[3]);
-                    rw.z = pack_half2(o[4], o[5]); rw.w = pack_half2(o[6], o[7]);
-                    p.out[row + (long long)cb * 4 * p.gout.Lp] = rw;
-                }
+                for (int j = 0; j < 8; j++)
+                    o[j] = fmaxf(fmaf(__uint_as_float(v[j]), scale[cb * 8 + j], offs[cb * 8 + j]), 0.f);   // bias+BN, then the consumer's ReLU
+                uint4 rw;
+                rw.x = pack_half2(o[0], o[1]); rw.y = pack_half2(o[2], o[3]);
+                rw.z = pack_half2(o[4], o[5]); rw.w = pack_half2(o[6], o[7]);
+                p.out[row + (long long)cb * 4 * p.gout.Lp] = rw;
             }
         }
     }
 }
 
 template <class C>
-__device__ __forceinline__ void epilogue_head(const LayerParams &p, const float *epi, uint32_t taddr, int pp) {
+__device__ __forceinline__ void epilogue_head(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int ph) {
     const Geom &gi = p.gin;
     const int n = pp / gi.S;
     const int r = pp - n * gi.S;
     const int y2 = r / gi.P, x2 = r - y2 * gi.P;
     const float c0 = epi[0];
+    uint32_t v[4];
+    tmem_ld4(taddr + (uint32_t)(ph * C::NCOLS), v);
+    tmem_wait_ld();
+    const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);
+    const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
 #pragma unroll
-    for (int ph = 0; ph < 4; ph++) {
-        uint32_t v[4];
-        tmem_ld4(taddr + (uint32_t)(ph * C::NCOLS), v);
-        tmem_wait_ld();
-        const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);
-        const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
-#pragma unroll
-        for (int par = 0; par < 4; par++) {
-            const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
-            if (vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt) {
-                const float z = __uint_as_float(v[par]) + c0;
-                const size_t o = ((size_t)n * p.Ht + Y) * p.Wt + X;
-                p.mask[o] = z > 0.f ? 1 : 0;      // sigmoid(z) > 0.5 (nvinfer threshold), +1 of maskcopy folded
-                if (p.logits) p.logits[o] = z;
-            }
+    for (int par = 0; par < 4; par++) {
+        const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
+        if (vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt) {
+            const float z = __uint_as_float(v[par]) + c0;
+            const size_t o = ((size_t)n * p.Ht + Y) * p.Wt + X;
+            p.mask[o] = z > 0.f ? 1 : 0;      // sigmoid(z) > 0.5 (nvinfer threshold), +1 of maskcopy folded
+            if (p.logits) p.logits[o] = z;
         }
     }
 }
@@ -353,9 +359,9 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(kMaxStage + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kMaxStage + s); };
-    auto tempty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kMaxStage + 4 + s); };
-    const uint32_t w_bar = bar0 + 8u * (uint32_t)(2 * kMaxStage + 8);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + sp.bar_off + 8 * (2 * kMaxStage + 9));
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kMaxStage + 8 + s); };
+    const uint32_t w_bar = bar0 + 8u * (uint32_t)(2 * kMaxStage + 16);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + sp.bar_off + 8 * (2 * kMaxStage + 17));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStage; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 4; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 8; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * C::CG); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -439,24 +445,28 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
         }
     } else {
         // ===== epilogue warps: TMEM -> registers -> fused layer tail -> HBM =====
-        const int q = warp & 3;
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int gidx = (warp - 2) >> 2;             // warp group 0..3
+        const int cg = gidx % C::CG, tg = gidx / C::CG;
         uint32_t tile_it = 0;
         for (int g = cta; g < p.n_groups; g += n_cta) {
 #pragma unroll 1
             for (int j = 0; j < C::TPS; j++) {
                 const int tile = g * C::TPS + j;
                 if (tile >= p.n_tiles) break;
-                const int slot = (int)(tile_it % (uint32_t)C::NSLOT);
-                mbar_wait(tfull_bar(slot), (tile_it / (uint32_t)C::NSLOT) & 1u, p.watchdog, 5u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * C::COLS_TILE);
-                const int pp = tile * kTileM + q * 32 + lane;
-                if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, taddr, pp, lane);
-                else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half);
-                else epilogue_head<C>(p, epi, taddr, pp);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(slot));
+                if ((int)(tile_it % (uint32_t)C::TG) == tg) {
+                    const int slot = (int)(tile_it % (uint32_t)C::NSLOT);
+                    mbar_wait(tfull_bar(slot), (tile_it / (uint32_t)C::NSLOT) & 1u, p.watchdog, 5u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * C::COLS_TILE);
+                    const int pp = tile * kTileM + q * 32 + lane;
+                    if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, taddr, pp, lane, cg);
+                    else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half, cg);
+                    else epilogue_head<C>(p, epi, taddr, pp, cg);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(slot));
+                }
                 tile_it++;
             }
         }

@@ -223,23 +223,31 @@ class BlobPipeline:
     def sync(self):
         check(_lib.load().cova_pipeline_sync(self._h))
 
-    def fetch_boxes(self) -> list[bytes]:
+    def fetch_boxes_raw(self, blob_cap: int | None = None):
+        """(blob, offsets, lens): window i's bincode(Vec<Bbox>) is blob[offsets[i] : offsets[i] + lens[i]].
+        The arrays are reused by the next call.  `blob_cap` bounds the host arena (default: worst case)."""
         n = self.n_windows
-        cap = n * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
+        cap = blob_cap or n * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
         if self._blob is None or self._blob.size < cap:
             self._blob = np.empty(max(cap, 8), dtype=np.uint8)
-        offs = np.zeros(max(n, 1), dtype=np.uint64)
-        lens = np.zeros(max(n, 1), dtype=np.uint64)
+            self._offs = np.zeros(max(self.max_streams * self.max_fps, 1), dtype=np.uint64)
+            self._lens = np.zeros(max(self.max_streams * self.max_fps, 1), dtype=np.uint64)
         ln = ctypes.c_size_t()
-        check(_lib.load().cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens)))
+        check(_lib.load().cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln),
+                                                    _ptr(self._offs), _ptr(self._lens)))
         self.last_blob_len = ln.value
-        return [self._blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs[:n], lens[:n])]
+        return self._blob, self._offs[:n], self._lens[:n]
 
-    def process(self, frames: np.ndarray) -> list[bytes]:
-        """Host frames -> list of bincode(Vec<Bbox>) blobs, one per window (stream-major, time-minor)."""
+    def fetch_boxes(self) -> list[bytes]:
+        blob, offs, lens = self.fetch_boxes_raw()
+        return [blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs, lens)]
+
+    def process(self, frames: np.ndarray, raw: bool = False, blob_cap: int | None = None):
+        """Host frames -> per-window bincode(Vec<Bbox>) blobs (stream-major, time-minor): a list of bytes,
+        or with raw=True the (blob, offsets, lens) arrays without per-window Python objects."""
         self.load_frames(frames)
         self.run()
-        return self.fetch_boxes()
+        return self.fetch_boxes_raw(blob_cap) if raw else self.fetch_boxes()
 
     # ---- inspection (parity tests)
     def read_stacked(self) -> np.ndarray:

@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(cova_b200/_lib.py -> libcova_b200.so); the oracle is only the checker."""
+import os
+
+import numpy as np
+import pytest
+
+from cova_b200 import _lib, synth, weights
+from cova_b200.elements import FLOW_DROPPED, FLOW_OK, BboxCc, BlobPipeline, MetaPreprocess, deserialize_vec
+from oracle import bboxcc_ref, blobnet_ref, c_oracle, metapreprocess_ref as mpr
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "ccl_golden.npz"))
+META = [m.split(",") for m in G["meta"]]
+
+# floating-point bars (BASELINE.json north_star): logits within fp16 tolerance of the fp32 oracle and at
+# most 0.1 % of mask pixels flipping.  fp16 operands / fp32 accumulation over 8 layers: 2e-2 of the
+# logit scale is ~25x the error actually observed.
+LOGIT_REL_TOL = 2e-2
+ACT_REL_TOL = 1e-2
+MAX_FLIP = 1e-3
+
+
+def golden_case(i):
+    h, w, name, n = META[i]
+    h, w, n = int(h), int(w), int(n)
+    raw = G[f"raw_{i}"]
+    m = raw.reshape(h, w) if raw.size else np.unpackbits(G[f"mask_{i}"])[: h * w].reshape(h, w)
+    return h, w, name, n, m, G[f"labels_{i}"].astype(np.int32), G[f"stats_{i}"]
+
+
+# ----------------------------------------------------------------------------------------- metapreprocess
+@pytest.mark.parametrize("T,gamma", [(1, 1), (2, 1), (4, 1), (4, 2), (4, 3), (3, 5)])
+def test_metapreprocess_element_bit_exact(T, gamma):
+    fr = synth.synth_stream(17, 45, 80, seed=T * 10 + gamma)
+    el, ref = MetaPreprocess(1280, 720, T, gamma), mpr.MetaPreprocessRef(1280, 720, T, gamma)
+    assert el.transform_caps() == {"format": "RGBA", "width": 80, "height": 45 * T}
+    flows = []
+    for f in range(fr.shape[0]):
+        got, want = el.transform(fr[f]), ref.transform(fr[f])
+        assert got == want
+        flows.append(got[0])
+    assert flows[: T - 1] == [FLOW_DROPPED] * (T - 1) and FLOW_OK in flows
+
+
+def test_metapreprocess_1080p_caps_and_prefix():
+    el = MetaPreprocess(1920, 1080, 4, 1)
+    assert (el.out_width, el.out_height) == (120, 67 * 4)          # integer division: 67 rows, not 68
+    rng = np.random.default_rng(0)
+    ref = mpr.MetaPreprocessRef(1920, 1080, 4, 1)
+    for _ in range(6):
+        buf = rng.integers(0, 256, 1920 * 1080 * 3 // 2, dtype=np.uint8)   # a whole I420 buffer
+        assert el.transform(buf) == ref.transform(buf)
+
+
+def test_metapreprocess_gamma_property_is_mutable():
+    fr = synth.synth_stream(12, 45, 80, seed=1)
+    el, ref = MetaPreprocess(1280, 720, 4, 1), mpr.MetaPreprocessRef(1280, 720, 4, 1)
+    for f in range(12):
+        if f == 6:
+            el.set_property("gamma", 3)
+            ref.gamma = 3
+        assert el.transform(fr[f]) == ref.transform(fr[f])
+    assert el.get_property("gamma") == 3
+
+
+# ----------------------------------------------------------------------------------------- bboxcc
+_ELS = {}
+
+
+def _bboxcc(w, h):
+    if (w, h) not in _ELS:
+        _ELS[(w, h)] = BboxCc(w, h, 1)
+    return _ELS[(w, h)]
+
+
+@pytest.mark.parametrize("i", range(len(META)))
+def test_bboxcc_matches_opencv_golden(i):
+    h, w, name, n, m, labels, stats = golden_case(i)
+    el = _bboxcc(w, h)
+    n2, l2, s2 = el.labels(m)
+    assert n2 == n and (l2 == labels).all(), name
+    if n > 1:
+        assert (s2[1:] == stats).all(), name
+    for thr in (0, 1, 3, 30):
+        el.set_property("cc-threshold", thr)
+        assert el.get_property("cc-threshold") == thr
+        want = bboxcc_ref.serialize_vec([bboxcc_ref.bbox_new(*stats[k, :4]) for k in range(n - 1) if stats[k, 4] >= thr])
+        assert el.transform_ip(m) == want, (name, thr)
+
+
+def test_bboxcc_default_threshold_and_errors():
+    el = BboxCc(80, 45)
+    assert el.get_property("cc-threshold") == 30                    # bboxcc/imp.rs:16
+    with pytest.raises(_lib.CovaError) as e:
+        el.transform_ip(np.zeros(10, np.uint8))
+    assert e.value.code == _lib.E_INVAL
+    el.set_property("cc-threshold", 0xFFFFFFFF)                     # `as i32` -> -1: everything passes
+    m = synth.mask_patterns(45, 80, 3)["bernoulli_0.2"]
+    assert el.transform_ip(m) == bboxcc_ref.bboxcc_transform_ref(m, 80, 45, 0)
+
+
+@pytest.mark.parametrize("h,w", [(45, 80), (68, 120), (135, 240)])
+def test_pipeline_ccl_batch_matches_oracle(h, w):
+    pats = synth.mask_patterns(h, w, seed=7)
+    rng = np.random.default_rng(1)
+    masks = np.stack(list(pats.values()) + [(rng.random((h, w)) < p).astype(np.uint8) for p in rng.uniform(0.02, 0.7, 15)])
+    blob = weights.to_blob(weights.random_weights(0))
+    p = BlobPipeline(w, h, blob, masks.shape[0], 5, cc_threshold=1)    # capacity: 2 windows per chain
+    for thr in (1, 4):
+        p.set_property("cc-threshold", thr)
+        for lo in range(0, masks.shape[0], p.max_streams * 2):
+            chunk = masks[lo: lo + p.max_streams * 2]
+            p.load_masks(chunk)
+            p.ccl()
+            got = p.fetch_boxes()
+            want = c_oracle.bboxcc_batch(chunk, thr)
+            assert got == want
+
+
+# ----------------------------------------------------------------------------------------- tensorise + BlobNet
+def _oracle(w, frames):
+    stacked = np.concatenate([mpr.tensorise_stream(frames[s], 4, 1) for s in range(frames.shape[0])])
+    x = mpr.stacked_to_nchw(stacked, 4)
+    logit, inter = blobnet_ref.blobnet_forward(w, x, return_intermediates=True)
+    refs = {0: np.clip(x, 0, 6), 1: inter["enc0"], 2: inter["enc1"], 3: inter["enc2"], 4: inter["enc3"][:, :, :1],
+            5: np.maximum(inter["dec0"], 0)[:, :, None], 6: np.maximum(inter["dec1"], 0)[:, :, None],
+            7: np.maximum(inter["dec2"], 0)[:, :, None]}
+    return stacked, logit, refs
+
+
+@pytest.mark.parametrize("h,w,n_streams,fps,seed", [(45, 80, 3, 9, 0), (67, 120, 1, 6, 1), (68, 120, 1, 5, 2),
+                                                    (16, 16, 2, 5, 3), (21, 37, 2, 6, 4), (135, 240, 1, 4, 5)])
+def test_tensorise_and_blobnet_against_oracle(h, w, n_streams, fps, seed):
+    wts = weights.random_weights(seed, head_bias=-1.0)
+    frames = synth.synth_streams(n_streams, fps, h, w, config_idx=seed)
+    stacked, logit_ref, refs = _oracle(wts, frames)
+    p = BlobPipeline(w, h, weights.to_blob(wts), n_streams, fps, impl=_lib.IMPL_TCGEN05, keep_logits=True, keep_stacked=True)
+    boxes = p.process(frames)
+    assert (p.read_stacked() == stacked).all()                      # tensorised windows: bit-exact
+    assert (p.read_activation(0) == refs[0]).all()                  # BlobNet input layout: bit-exact
+    for layer in range(1, 8):
+        a = p.read_activation(layer)
+        assert a.shape == refs[layer].shape
+        err = np.abs(a - refs[layer]).max() / (np.abs(refs[layer]).max() + 1e-12)
+        assert err < ACT_REL_TOL, (layer, err)
+    logits, mask = p.read_logits(), p.read_mask()
+    assert np.abs(logits - logit_ref).max() <= LOGIT_REL_TOL * np.abs(logit_ref).max()
+    assert ((logits > 0) != (logit_ref > 0)).mean() <= MAX_FLIP
+    assert (mask == (logits > 0)).all()
+    assert set(np.unique(mask)) <= {0, 1}                           # maskcopy's class_map + 1
+    for i, b in enumerate(boxes):                                   # boxes: bit-exact for the given mask
+        assert b == bboxcc_ref.bboxcc_transform_ref(mask[i], w, h, 1)
+        for box in deserialize_vec(b):
+            assert box[4] == box[2] * box[3]
+
+
+def test_tcgen05_layers_match_validation_kernels_layer_by_layer():
+    wts = weights.random_weights(11, head_bias=-1.0)
+    frames = synth.synth_streams(2, 8, 45, 80, config_idx=2)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 2, 8, impl=_lib.IMPL_SIMT, keep_logits=True)
+    p.load_frames(frames)
+    p.run()
+    ref_act = {layer: p.read_activation(layer) for layer in range(8)}
+    ref_logits = p.read_logits()
+    for layer in range(8):
+        p.run_layer(layer, _lib.IMPL_TCGEN05)
+        if layer < 7:
+            a = p.read_activation(layer + 1)
+            assert np.abs(a - ref_act[layer + 1]).max() <= 4e-3 * np.abs(ref_act[layer + 1]).max(), layer
+            p.run_layer(layer, _lib.IMPL_SIMT)
+        else:
+            assert np.abs(p.read_logits() - ref_logits).max() <= 4e-3 * np.abs(ref_logits).max()
+
+
+def test_gamma_subsampling_and_chain_restart():
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.synth_streams(2, 11, 45, 80, config_idx=3)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 2, 11, gamma=3, keep_stacked=True)
+    p.process(frames)
+    want = np.concatenate([mpr.tensorise_stream(frames[s], 4, 3) for s in range(2)])
+    assert p.n_windows == want.shape[0] == 2 * 3
+    assert (p.read_stacked() == want).all()
+
+
+def test_pipeline_is_deterministic_and_reusable():
+    wts = weights.random_weights(0, head_bias=-1.0)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 4, 10)
+    a = synth.synth_streams(4, 10, 45, 80, config_idx=4)
+    b = synth.synth_streams(2, 7, 45, 80, config_idx=5)
+    ra1, rb, ra2 = p.process(a), p.process(b), p.process(a)
+    assert ra1 == ra2 and len(rb) == 2 * 4
+    assert p.launch_count() == 3 * 10
+
+
+def test_byte3_and_values_above_six_do_not_matter():
+    """byte 3 is stale decoder garbage and BlobNet clips at 6 (preprocessing.py:5-8)."""
+    wts = weights.random_weights(2, head_bias=-1.0)
+    frames = synth.synth_streams(1, 6, 45, 80, config_idx=6)
+    alt = frames.copy()
+    alt[..., 3] = 255 - alt[..., 3]
+    big = alt[..., :3] >= 6
+    alt[..., :3][big] = 200
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 1, 6, keep_logits=True)
+    p.process(frames)
+    l1 = p.read_logits()
+    p.process(alt)
+    assert (p.read_logits() == l1).all()
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[1] scale (64-window chains): size-independent checks instead of the slow oracle:
+    boxes are bit-exact for the device mask via the C oracle, every window of an identical chain gives
+    identical output, and a second run reproduces the first."""
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.tiled_streams(16, 67, 45, 80, config_idx=1, n_unique=4)
+    frames[8:] = frames[:8]                                         # chains 8..15 duplicate chains 0..7
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 16, 67)
+    blobs = p.process(frames)
+    mask = p.read_mask()
+    assert len(blobs) == 16 * 64
+    assert blobs == c_oracle.bboxcc_batch(mask, 1)
+    assert blobs[: 8 * 64] == blobs[8 * 64:]
+    assert (mask[: 8 * 64] == mask[8 * 64:]).all()
+    assert 0.01 < mask.mean() < 0.5
+    assert p.process(frames) == blobs
