@@ -67,6 +67,7 @@ SIGNATURES = {
     "cova_pipeline_read_logits": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "cova_pipeline_read_activation": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _u32p]),
     "cova_pipeline_run_layer": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_uint32]),
+    "cova_pipeline_set_debug": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cova_pipeline_launch_count": (ctypes.c_int, [_vp, _u64p]),
     "cova_pipeline_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cova_pipeline_last_timings": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t, _f32p, _u32p]),

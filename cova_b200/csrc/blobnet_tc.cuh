@@ -26,6 +26,7 @@ constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2;
 constexpr int kMaxStage = 4;
 constexpr int kEpiWarps = 16;                 // 4 groups of 4 warps (one per TMEM lane quarter)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kScratchPitch = 36;              // floats per channel row of the quad-exchange scratch (32 lanes + 4: conflict-free 128-bit reads)
 
 struct LayerParams {
     const uint4 *in; Geom gin;
@@ -44,6 +45,8 @@ struct LayerParams {
     int Ht, Wt, crop_t, crop_l;        // DEC/HEAD: target extent and crop
     uint8_t *mask; float *logits;      // HEAD
     unsigned int *watchdog;            // set to a non-zero code if a barrier wait times out
+    int bn_nonneg;                     // ENC: every BatchNorm scale of the layer is >= 0 (skips the min-pool path)
+    int dbg;                           // experiments only: bit0 = skip the MMAs, bit1 = skip the epilogue math (results are garbage)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -74,6 +77,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
             __trap();
         }
     }
+}
+// One elected lane of a fully converged warp.  Unlike `lane == 0`, elect.sync tells ptxas that exactly one
+// thread runs the guarded code, so descriptors can go to uniform registers without a waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -158,7 +172,8 @@ __host__ __device__ inline SmemPlan plan_smem(int Ls, int n_stage, int w_bytes, 
 }
 template <class C>
 __host__ __device__ constexpr int epi_floats() {
-    return C::MODE == MODE_ENC ? 3 * C::COUT + 32 : (C::MODE == MODE_DEC ? 2 * C::COUT : 4);
+    // encoder: bias|scale|shift, two 4x4 TN matrices, then 256 floats of exchange scratch per epilogue warp
+    return C::MODE == MODE_ENC ? 3 * C::COUT + 32 + kEpiWarps * 8 * kScratchPitch : (C::MODE == MODE_DEC ? 2 * C::COUT : 4);
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issue
@@ -223,26 +238,33 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
+// Encoder tail for one 128-position tile and one group of channel blocks.  Lane = (position, t): the four
+// frames of a window position are the four lanes of a quad.
+//   1. bias -> ReLU -> BatchNorm -> 2x2 max-pool over the four phase accumulators, per lane, in registers;
+//   2. PointWiseTN needs all four t of a (position, channel): the quad exchanges its 8 channels x 4 t through a
+//      1.1 KB per-warp shared-memory scratch ([channel][lane] floats, padded rows: conflict-free stores, one 128-bit load per
+//      channel) and each lane then computes TWO channels for ALL four output frames - no redundant 4x4
+//      products and no shuffles;
+//   3. each lane stores its 2-channel slice (4 bytes) of the four 16-byte output rows of the quad.
 template <class C>
-__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int lane, int cg) {
+__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, float *scratch, uint32_t taddr, int pp,
+                                             int lane, int cg) {
     const Geom &gi = p.gin;
     const int t = pp & 3;
     const int qq = pp >> 2;
     const int n = qq / gi.S;
     const int r = qq - n * gi.S;
     const int y2 = r / gi.P, x2 = r - y2 * gi.P;
-    const bool valid = n < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);
+    const bool valid = n < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);   // same for the 4 lanes of a quad
     const int Y = y2 + (gi.H & 1), X = x2 + (gi.W & 1);          // zero-pad top / left when odd (encoder.py:68-76)
     const int pho = ((Y & 1) << 1) | (X & 1);
-    long long row1 = 0, row2 = 0;
+    uint32_t *dst1 = nullptr, *dst2 = nullptr;                   // this lane's 4-byte slice of row (quad, t' = 0)
     if (valid) {
-        if (p.out) row1 = geom_row(p.gout, 0, pho, geom_pos(p.gout, n, Y >> 1, X >> 1, t));
-        if (p.out2) row2 = geom_row(p.gout2, p.out2_cb, pho, geom_pos(p.gout2, n, Y >> 1, X >> 1, 0));
+        if (p.out) dst1 = reinterpret_cast<uint32_t *>(p.out + geom_row(p.gout, 0, pho, geom_pos(p.gout, n, Y >> 1, X >> 1, 0))) + t;
+        if (p.out2) dst2 = reinterpret_cast<uint32_t *>(p.out2 + geom_row(p.gout2, p.out2_cb, pho, geom_pos(p.gout2, n, Y >> 1, X >> 1, 0))) + t;
     }
-    const float *bias = epi, *scale = epi + C::COUT, *shift = epi + 2 * C::COUT, *w2s = epi + 3 * C::COUT + 16;
-    float w2c[4];
-#pragma unroll
-    for (int m = 0; m < 4; m++) w2c[m] = w2s[m * 4 + t];          // column t of W2
+    const float4 *bias4 = reinterpret_cast<const float4 *>(epi), *scale4 = reinterpret_cast<const float4 *>(epi + C::COUT),
+                 *shift4 = reinterpret_cast<const float4 *>(epi + 2 * C::COUT);
     const int qbase = lane & ~3;
     constexpr int CB_PER = (C::COUT / 8) / C::CG;                 // channel blocks of this warp group
 #pragma unroll 1
@@ -250,40 +272,60 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
         uint32_t v[4][8];
 #pragma unroll
         for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
+        float bs[8], sc[8], sh[8];
+        *reinterpret_cast<float4 *>(bs) = bias4[cb * 2]; *reinterpret_cast<float4 *>(bs + 4) = bias4[cb * 2 + 1];
+        *reinterpret_cast<float4 *>(sc) = scale4[cb * 2]; *reinterpret_cast<float4 *>(sc + 4) = scale4[cb * 2 + 1];
+        *reinterpret_cast<float4 *>(sh) = shift4[cb * 2]; *reinterpret_cast<float4 *>(sh + 4) = shift4[cb * 2 + 1];
         tmem_wait_ld();
-        float o[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int c = cb * 8 + j;
-            const float b = bias[c], s = scale[c], sh = shift[c];
             // MaxPool(BN(ReLU(x + b))): x -> fma(max(x + b, 0), s, sh) is monotone (non-decreasing for s >= 0,
             // non-increasing for s < 0), so the pool maximum is attained at max(x) resp. min(x): bit-identical
             // to pooling the four activated values, with a quarter of the arithmetic.
             const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
             const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
-            const float hi = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), lo = fminf(fminf(a0, a1), fminf(a2, a3));
-            const float m = fmaf(fmaxf((s >= 0.f ? hi : lo) + b, 0.f), s, sh);
-            // PointWiseTN: the 4 frames of this window position are the 4 lanes of this quad
-            float xs[4];
-#pragma unroll
-            for (int ti = 0; ti < 4; ti++) xs[ti] = __shfl_sync(0xffffffffu, m, qbase + ti);
-            float h2 = 0.f;
-#pragma unroll
-            for (int mm = 0; mm < 4; mm++) {
-                float h1 = 0.f;
-#pragma unroll
-                for (int ti = 0; ti < 4; ti++) h1 = fmaf(xs[ti], p.tn_w1[ti * 4 + mm], h1);
-                h2 = fmaf(fmaxf(h1, 0.f), w2c[mm], h2);
+            float ext = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            if (!p.bn_nonneg) {
+                const float lo = fminf(fminf(a0, a1), fminf(a2, a3));
+                ext = sc[j] >= 0.f ? ext : lo;
             }
-            o[j] = fmaxf(m + fmaxf(h2, 0.f), 0.f);
+            scratch[j * kScratchPitch + lane] = fmaf(fmaxf(ext + bs[j], 0.f), sc[j], sh[j]);
         }
+        __syncwarp();
+        // PointWiseTN (pointwise.py:18-26) for channels 2t, 2t+1 of this quad's position, all four output frames
+        uint32_t packed[4];
+        float y[2][4];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const float4 x4 = *reinterpret_cast<const float4 *>(scratch + (2 * t + c) * kScratchPitch + qbase);
+            const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+            float h1[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                float h = 0.f;
+#pragma unroll
+                for (int ti = 0; ti < 4; ti++) h = fmaf(x[ti], p.tn_w1[ti * 4 + m], h);
+                h1[m] = fmaxf(h, 0.f);
+            }
+#pragma unroll
+            for (int to = 0; to < 4; to++) {
+                float h = 0.f;
+#pragma unroll
+                for (int m = 0; m < 4; m++) h = fmaf(h1[m], p.tn_w2[m * 4 + to], h);
+                y[c][to] = fmaxf(x[to] + fmaxf(h, 0.f), 0.f);
+            }
+        }
+#pragma unroll
+        for (int to = 0; to < 4; to++) packed[to] = pack_half2(y[0][to], y[1][to]);
         if (valid) {
-            uint4 row;
-            row.x = pack_half2(o[0], o[1]); row.y = pack_half2(o[2], o[3]);
-            row.z = pack_half2(o[4], o[5]); row.w = pack_half2(o[6], o[7]);
-            if (p.out) p.out[row1 + (long long)cb * 4 * p.gout.Lp] = row;
-            if (p.out2 && t == 0) p.out2[row2 + (long long)cb * 4 * p.gout2.Lp] = row;
+            if (p.out) {
+                uint32_t *d = dst1 + (long long)cb * 4 * p.gout.Lp * 4;   // rows are 4 x u32
+#pragma unroll
+                for (int to = 0; to < 4; to++) d[to * 4] = packed[to];    // rows t' = 0..3 are consecutive
+            }
+            if (p.out2) dst2[(long long)cb * 4 * p.gout2.Lp * 4] = packed[0];
         }
+        __syncwarp();
     }
 }
 
@@ -369,7 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     const int cta = (int)blockIdx.x / nsplit, n_cta = (int)gridDim.x / nsplit;
 
     // epilogue constants -> smem (generic proxy)
-    for (int i = threadIdx.x; i < epi_floats<C>(); i += kThreads) {
+    constexpr int kEpiConst = C::MODE == MODE_ENC ? 3 * C::COUT + 32 : epi_floats<C>();
+    for (int i = threadIdx.x; i < kEpiConst; i += kThreads) {
         float v;
         if (C::MODE == MODE_ENC && i >= 3 * C::COUT) v = (i - 3 * C::COUT < 16) ? p.tn_w1[i - 3 * C::COUT] : p.tn_w2[i - 3 * C::COUT - 16];
         else v = p.epi[i];
@@ -392,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
 
     if (warp == 0) {
         // ===== producer: weights once, then one strip per (group, k-chunk) =====
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
             bulk_g2s(smem_base + sp.w_off, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)half * p.w_bytes,
                      (uint32_t)p.w_bytes, w_bar);
@@ -414,8 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer (one elected thread) =====
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc(C::NCOLS);
             mbar_wait(w_bar, 0u, p.watchdog, 2u);
             uint32_t it = 0, tile_it = 0;
@@ -435,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                             mbar_wait(tempty_bar(slot), ((tile_it / (uint32_t)C::NSLOT) & 1u) ^ 1u, p.watchdog, 4u);
                             tc_fence_after();
                         }
-                        issue_tile<C>(p, stage_addr, smem_base + sp.w_off, tmem_base + (uint32_t)(slot * C::COLS_TILE), j, kc, idesc);
+                        if (!(p.dbg & 1)) issue_tile<C>(p, stage_addr, smem_base + sp.w_off, tmem_base + (uint32_t)(slot * C::COLS_TILE), j, kc, idesc);
                         if (kc == C::NKC - 1) umma_commit(tfull_bar(slot));
                         tile_it++;
                     }
@@ -448,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int gidx = (warp - 2) >> 2;             // warp group 0..3
         const int cg = gidx % C::CG, tg = gidx / C::CG;
+        float *scratch = epi + 3 * C::COUT + 32 + (warp - 2) * 8 * kScratchPitch;   // encoder only
         uint32_t tile_it = 0;
         for (int g = cta; g < p.n_groups; g += n_cta) {
 #pragma unroll 1
@@ -460,7 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * C::COLS_TILE);
                     const int pp = tile * kTileM + q * 32 + lane;
-                    if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, taddr, pp, lane, cg);
+                    if (p.dbg & 2) {
+                    } else if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, scratch, taddr, pp, lane, cg);
                     else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half, cg);
                     else epilogue_head<C>(p, epi, taddr, pp, cg);
                     tc_fence_before();

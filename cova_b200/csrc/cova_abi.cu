@@ -336,6 +336,7 @@ struct cova_pipeline {
     std::vector<float> last_ms;
     size_t ev_used = 0;
     uint64_t launches = 0;
+    int dbg = 0;
 };
 
 static uint32_t windows_per_stream(uint32_t fps, uint32_t T, uint32_t gamma) {
@@ -631,7 +632,7 @@ static int tc_layer(cova_pipeline *p, int layer) {
     const int N = (int)p->cur_windows;
     LayerParams lp;
     memset(&lp, 0, sizeof(lp));
-    lp.N = N; lp.watchdog = p->d_watchdog;
+    lp.N = N; lp.watchdog = p->d_watchdog; lp.dbg = p->dbg;
     int rc;
     if (layer < 4) {
         const int i = layer;
@@ -644,6 +645,9 @@ static int tc_layer(cova_pipeline *p, int layer) {
         memcpy(lp.tn_w1, p->hw.enc[i].tn_w1, 64);
         memcpy(lp.tn_w2, p->hw.enc[i].tn_w2, 64);
         lp.nsplit = 1;
+        lp.bn_nonneg = 1;
+        for (int c = 0; c < kEncCout[i]; c++)
+            if (!(p->hw.enc[i].gamma[c] >= 0.f)) lp.bn_nonneg = 0;
         //                                  MODE   CIN_CB NCOLS TPS KCH COUT
         if (i == 0) rc = launch_first_fit<Cfg<MODE_ENC, 1, 16, 4, 1, 16>, Cfg<MODE_ENC, 1, 16, 2, 1, 16>, Cfg<MODE_ENC, 1, 16, 1, 1, 16>>(lp, p->n_sms, p->stream);
         else if (i == 1) rc = launch_first_fit<Cfg<MODE_ENC, 2, 32, 4, 2, 32>, Cfg<MODE_ENC, 2, 32, 2, 2, 32>, Cfg<MODE_ENC, 2, 32, 1, 2, 32>>(lp, p->n_sms, p->stream);
@@ -839,6 +843,11 @@ extern "C" int cova_pipeline_read_activation(cova_pipeline *p, int layer, float 
     return COVA_OK;
 }
 
+extern "C" int cova_pipeline_set_debug(cova_pipeline *p, int flags) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    p->dbg = flags;
+    return COVA_OK;
+}
 extern "C" int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count) {
     if (!p || !count) return set_err(COVA_E_INVAL, "null argument");
     *count = p->launches;

@@ -273,6 +273,9 @@ class BlobPipeline:
         shp = tuple(int(v) for v in shape)
         return out[: int(np.prod(shp))].reshape(shp).copy()
 
+    def set_debug(self, flags: int):
+        check(_lib.load().cova_pipeline_set_debug(self._h, flags))
+
     def launch_count(self) -> int:
         c = ctypes.c_uint64()
         check(_lib.load().cova_pipeline_launch_count(self._h, ctypes.byref(c)))

@@ -145,6 +145,8 @@ int cova_pipeline_read_activation(cova_pipeline *p, int layer, float *out, size_
  * implementation on whatever its input buffer currently holds - lets the tests compare the tcgen05
  * kernel of a layer against the validation kernel of the same layer on identical inputs */
 int cova_pipeline_run_layer(cova_pipeline *p, int layer, uint32_t impl);
+/* performance experiments only (results become garbage): bit0 skips the MMAs, bit1 the epilogue math */
+int cova_pipeline_set_debug(cova_pipeline *p, int flags);
 /* kernels launched by this handle since creation */
 int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count);
 /* per-kernel device time of the last cova_pipeline_run* with profiling enabled: names is a

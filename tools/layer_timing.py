@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Per-layer timing experiments (development aid): normal / MMA-only / epilogue-only."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cova_b200 import _lib, synth, weights
+from cova_b200.elements import BlobPipeline
+
+n_streams, fps = int(os.environ.get("STREAMS", 128)), 67
+h, w = int(os.environ.get("H", 45)), int(os.environ.get("W", 80))
+p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps)
+p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
+p.set_profiling(True)
+res = {}
+for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither", 3)):
+    p.set_debug(flags)
+    acc = {}
+    for _ in range(4):
+        p.run(); p.sync()
+        for k, v in p.last_timings().items():
+            acc.setdefault(k, []).append(v)
+    res[name] = {k: float(np.mean(v[1:])) for k, v in acc.items()}
+keys = list(res["normal"])
+print(f"{'kernel':16s}" + "".join(f"{n:>14s}" for n in res))
+for k in keys:
+    print(f"{k:16s}" + "".join(f"{res[n][k]:14.4f}" for n in res))
+print(f"{'total':16s}" + "".join(f"{sum(res[n].values()):14.4f}" for n in res), " windows", p.n_windows)
