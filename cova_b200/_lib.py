@@ -35,6 +35,8 @@ SIGNATURES = {
     "cova_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "cova_last_error": (ctypes.c_char_p, []),
     "cova_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "cova_host_alloc": (ctypes.c_int, [_vpp, ctypes.c_size_t]),
+    "cova_host_free": (None, [_vp]),
     "cova_metapreprocess_new": (ctypes.c_int, [_vpp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "cova_metapreprocess_free": (None, [_vp]),
     "cova_metapreprocess_set_gamma": (ctypes.c_int, [_vp, ctypes.c_uint32]),
@@ -61,6 +63,8 @@ SIGNATURES = {
     "cova_pipeline_sync": (ctypes.c_int, [_vp]),
     "cova_pipeline_fetch_boxes": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp]),
     "cova_pipeline_process_host": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p]),
+    "cova_pipeline_submit_host": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    "cova_pipeline_collect_host": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p]),
     "cova_pipeline_load_masks": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_int]),
     "cova_pipeline_read_stacked": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "cova_pipeline_read_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),

@@ -22,7 +22,7 @@
 namespace cova {
 namespace tc {
 
-constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2;
+constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2, MODE_ENCF = 3;   // ENCF: first conv, per FRAME (no PointWiseTN)
 constexpr int kMaxStage = 4;
 constexpr int kEpiWarps = 16;                 // 4 groups of 4 warps (one per TMEM lane quarter)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
@@ -138,20 +138,22 @@ __host__ __device__ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 
 template <int MODE_, int CIN_CB_, int NCOLS_, int TPS_, int KCH_, int COUT_>
 struct Cfg {
     static constexpr int MODE = MODE_, CIN_CB = CIN_CB_, NCOLS = NCOLS_, TPS = TPS_, KCH = KCH_, COUT = COUT_;
+    static constexpr bool ENCF = MODE == MODE_ENCF;
     static constexpr int NKC = CIN_CB / KCH;
+    static constexpr int NPLANE = ENCF ? 2 : 4;                          // phase planes staged per channel block
     static constexpr int COLS_TILE = 4 * NCOLS;
     static constexpr int NSLOT = (512 / COLS_TILE) < 8 ? (512 / COLS_TILE) : 8;
     // the 4 epilogue warp groups split a tile by channel group (CG) and, when a tile has fewer than 4
     // channel blocks, also take alternate tiles (TG); decoder / head groups take one input phase each
-    static constexpr int CG = MODE_ == MODE_ENC ? ((COUT_ / 8) < 4 ? (COUT_ / 8) : 4) : 4;
+    static constexpr int CG = (MODE_ == MODE_ENC || ENCF) ? ((COUT_ / 8) < 4 ? (COUT_ / 8) : 4) : 4;
     static constexpr int TG = 4 / CG;
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * COLS_TILE);
-    static constexpr bool ENC1 = (MODE == MODE_ENC && CIN_CB == 1);
     static constexpr int NTAP = MODE == MODE_ENC ? 9 : 4;
-    static constexpr int KP = ENC1 ? 1 : KCH / 2;                        // K=16 steps per tap inside a stage
-    static constexpr int BLOCKS = ENC1 ? 20 : NTAP * (CIN_CB / 2);       // B blocks per N-half
+    static constexpr int KP = ENCF ? 1 : KCH / 2;                        // K=16 steps per tap inside a stage
+    static constexpr int BLOCKS = ENCF ? 6 : NTAP * (CIN_CB / 2);        // B blocks per N-half
+    static constexpr int BLOCK_N = ENCF ? 4 * NCOLS : NCOLS;             // rows of one B block (= N of one MMA)
     static_assert(NKC == 1 || TPS == 1, "accumulating over k-chunks needs one tile per stage");
-    static_assert(ENC1 || (KCH % 2 == 0), "a K=16 step spans two channel blocks");
+    static_assert(ENCF || (KCH % 2 == 0), "a K=16 step spans two channel blocks");
     static_assert(COLS_TILE <= 512, "accumulators exceed TMEM");
     static_assert(NSLOT >= TG, "tile-parallel epilogue groups need their own accumulator slots");
 };
@@ -164,7 +166,7 @@ __host__ __device__ inline SmemPlan plan_smem(int Ls, int n_stage, int w_bytes, 
     SmemPlan s;
     s.w_off = 0;
     s.stage_off = (uint32_t)((w_bytes + 127) / 128 * 128);
-    s.stage_bytes = (uint32_t)(C::KCH * 4 * Ls * 16);
+    s.stage_bytes = (uint32_t)(C::KCH * C::NPLANE * Ls * 16);
     s.epi_off = s.stage_off + (uint32_t)n_stage * s.stage_bytes;
     s.bar_off = s.epi_off + (uint32_t)((epi_floats * 4 + 15) / 16 * 16);
     s.total = s.bar_off + 8 * (2 * kMaxStage + 2 * 8 + 1) + 16;
@@ -173,7 +175,8 @@ __host__ __device__ inline SmemPlan plan_smem(int Ls, int n_stage, int w_bytes, 
 template <class C>
 __host__ __device__ constexpr int epi_floats() {
     // encoder: bias|scale|shift, two 4x4 TN matrices, then 256 floats of exchange scratch per epilogue warp
-    return C::MODE == MODE_ENC ? 3 * C::COUT + 32 + kEpiWarps * 8 * kScratchPitch : (C::MODE == MODE_DEC ? 2 * C::COUT : 4);
+    return C::MODE == MODE_ENC ? 3 * C::COUT + 32 + kEpiWarps * 8 * kScratchPitch
+                               : (C::MODE == MODE_ENCF ? 3 * C::COUT : (C::MODE == MODE_DEC ? 2 * C::COUT : 4));
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issue
@@ -183,30 +186,29 @@ template <class C>
 __device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_addr, uint32_t w_addr, uint32_t d_tmem,
                                            int tile_in_stage, int kc, uint32_t idesc) {
     const int Ls = p.Ls, P = p.gin.P, Tn = p.gin.Tn;
-    const uint32_t a_lbo = C::ENC1 ? 0u : (uint32_t)(4 * Ls * 16);
-    const uint64_t bdesc0 = make_desc(w_addr, (uint32_t)C::NCOLS * 16u, 128u);
     const int row0 = p.gin.halo + tile_in_stage * kTileM;
+    if constexpr (C::ENCF) {
+        // First conv on x-pair-packed rows ([c0 c1 c2 0 | c0' c1' c2' 0] = pixels (y, 2*x2), (y, 2*x2+1)), two row-parity
+        // planes.  An operand tile is (u = a+dy in -1..2, sx in -1..1); every MMA pairs two tiles through LBO (K = 16)
+        // and feeds all four phase accumulators at once (N = 64; unused (phase, tile) pairs have zero weights):
+        //   steps 0..3: (u, sx=-1) | (u, sx=0)  -> second K half is the next row, LBO = 16 B
+        //   steps 4..5: (u_lo, sx=+1) | (u_lo+2, sx=+1), same plane, one image row apart, LBO = P rows
+        const uint64_t bdesc0 = make_desc(w_addr, (uint32_t)C::BLOCK_N * 16u, 128u);
 #pragma unroll
-    for (int ph = 0; ph < 4; ph++) {
-        const int pa = ph >> 1, pb = ph & 1;
-        const uint32_t d = d_tmem + (uint32_t)(ph * C::NCOLS);
-        if constexpr (C::ENC1) {
+        for (int st = 0; st < 6; st++) {
+            const int u = st < 4 ? st - 1 : (st == 4 ? 0 : -1);
+            const int slot = u & 1;                                     // staged plane: row parity a'
+            const int r0 = slot * Ls + row0 + fdiv2(u) * P + (st < 4 ? -1 : 1);
+            const uint64_t adesc = make_desc(stage_addr + (uint32_t)r0 * 16u, st < 4 ? 16u : (uint32_t)P * 16u, 128u);
+            umma_f16(d_tmem, adesc, bdesc0 + (uint64_t)(st * C::BLOCK_N * 2), idesc, st > 0 ? 1u : 0u);
+        }
+    } else {
+        const uint32_t a_lbo = (uint32_t)(4 * Ls * 16);
+        const uint64_t bdesc0 = make_desc(w_addr, (uint32_t)C::NCOLS * 16u, 128u);
 #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                const Enc1Step s = enc1_step(pa, j);
-                const int plane0 = (((pa + s.dy0) & 1) << 1) | ((pb + s.dx0) & 1);
-                const int r0 = plane0 * Ls + row0 + (fdiv2(pa + s.dy0) * P + fdiv2(pb + s.dx0)) * Tn;
-                int lbo_rows = Tn;   // unused second half: any readable row
-                if (s.dy1 != 9) {
-                    const int plane1 = (((pa + s.dy1) & 1) << 1) | ((pb + s.dx1) & 1);
-                    const int r1 = plane1 * Ls + row0 + (fdiv2(pa + s.dy1) * P + fdiv2(pb + s.dx1)) * Tn;
-                    lbo_rows = r1 - r0;
-                }
-                const uint64_t adesc = make_desc(stage_addr + (uint32_t)r0 * 16u, (uint32_t)lbo_rows * 16u, 128u);
-                const uint64_t bdesc = bdesc0 + (uint64_t)((ph * 5 + j) * C::NCOLS * 2);   // block = NCOLS*32 B = NCOLS*2 x 16 B
-                umma_f16(d, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
-            }
-        } else {
+        for (int ph = 0; ph < 4; ph++) {
+            const int pa = ph >> 1, pb = ph & 1;
+            const uint32_t d = d_tmem + (uint32_t)(ph * C::NCOLS);
 #pragma unroll
             for (int tp = 0; tp < C::NTAP; tp++) {
                 int plane, sy, sx;
@@ -326,6 +328,50 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
             if (p.out2) dst2[(long long)cb * 4 * p.gout2.Lp * 4] = packed[0];
         }
         __syncwarp();
+    }
+}
+
+// First conv, per frame: bias -> ReLU -> BatchNorm -> 2x2 max-pool, stored as fp16 rows (pre-PointWiseTN)
+template <class C>
+__device__ __forceinline__ void epilogue_encf(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int cg) {
+    const Geom &gi = p.gin;
+    const int f = pp / gi.S;
+    const int r = pp - f * gi.S;
+    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const bool valid = f < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);
+    const int Y = y2 + (gi.H & 1), X = x2 + (gi.W & 1);          // zero-pad top / left when odd (encoder.py:68-76)
+    long long row = 0;
+    if (valid) row = geom_row(p.gout, 0, ((Y & 1) << 1) | (X & 1), geom_pos(p.gout, f, Y >> 1, X >> 1, 0));
+    const float4 *bias4 = reinterpret_cast<const float4 *>(epi), *scale4 = reinterpret_cast<const float4 *>(epi + C::COUT),
+                 *shift4 = reinterpret_cast<const float4 *>(epi + 2 * C::COUT);
+    constexpr int CB_PER = (C::COUT / 8) / C::CG;
+#pragma unroll 1
+    for (int cb = cg * CB_PER; cb < (cg + 1) * CB_PER; cb++) {
+        uint32_t v[4][8];
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
+        float bs[8], sc[8], sh[8], o[8];
+        *reinterpret_cast<float4 *>(bs) = bias4[cb * 2]; *reinterpret_cast<float4 *>(bs + 4) = bias4[cb * 2 + 1];
+        *reinterpret_cast<float4 *>(sc) = scale4[cb * 2]; *reinterpret_cast<float4 *>(sc + 4) = scale4[cb * 2 + 1];
+        *reinterpret_cast<float4 *>(sh) = shift4[cb * 2]; *reinterpret_cast<float4 *>(sh + 4) = shift4[cb * 2 + 1];
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
+            const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
+            float ext = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));      // see epilogue_enc: pool before the monotone ReLU/BN
+            if (!p.bn_nonneg) {
+                const float lo = fminf(fminf(a0, a1), fminf(a2, a3));
+                ext = sc[j] >= 0.f ? ext : lo;
+            }
+            o[j] = fmaf(fmaxf(ext + bs[j], 0.f), sc[j], sh[j]);
+        }
+        if (valid) {
+            uint4 rw;
+            rw.x = pack_half2(o[0], o[1]); rw.y = pack_half2(o[2], o[3]);
+            rw.z = pack_half2(o[4], o[5]); rw.w = pack_half2(o[6], o[7]);
+            p.out[row + (long long)cb * 4 * p.gout.Lp] = rw;
+        }
     }
 }
 
@@ -450,16 +496,16 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
 #pragma unroll 1
                     for (int cbi = 0; cbi < C::KCH; cbi++)
 #pragma unroll
-                        for (int ph = 0; ph < 4; ph++)
-                            bulk_g2s(dst0 + (uint32_t)((cbi * 4 + ph) * p.Ls) * 16u,
-                                     p.in + geom_row(p.gin, kc * C::KCH + cbi, ph, pos0), (uint32_t)p.Ls * 16u, full_bar(s));
+                        for (int pl = 0; pl < C::NPLANE; pl++)
+                            bulk_g2s(dst0 + (uint32_t)((cbi * C::NPLANE + pl) * p.Ls) * 16u,
+                                     p.in + geom_row(p.gin, kc * C::KCH + cbi, pl * (4 / C::NPLANE), pos0), (uint32_t)p.Ls * 16u, full_bar(s));
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) =====
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc(C::NCOLS);
+            constexpr uint32_t idesc = make_idesc(C::BLOCK_N);
             mbar_wait(w_bar, 0u, p.watchdog, 2u);
             uint32_t it = 0, tile_it = 0;
             for (int g = cta; g < p.n_groups; g += n_cta) {
@@ -506,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                     const int pp = tile * kTileM + q * 32 + lane;
                     if (p.dbg & 2) {
                     } else if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, scratch, taddr, pp, lane, cg);
+                    else if constexpr (C::MODE == MODE_ENCF) epilogue_encf<C>(p, epi, taddr, pp, cg);
                     else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half, cg);
                     else epilogue_head<C>(p, epi, taddr, pp, cg);
                     tc_fence_before();
@@ -525,20 +572,20 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
 constexpr int kSmemLimit = 227 * 1024;
 
 template <class C>
-inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &err) {
+inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &err, int min_stage) {
     const long long mtot = (long long)p.N * p.gin.S * p.gin.Tn;
     p.n_tiles = (int)((mtot + kTileM - 1) / kTileM);
     p.n_groups = (p.n_tiles + C::TPS - 1) / C::TPS;
     p.Ls = C::TPS * kTileM + 2 * p.gin.halo;
-    if (4 * p.Ls >= 16384) return false;                       // LBO field: 14 bits of 16-byte units
+    if (4 * p.Ls >= 16384 || p.gin.P >= 16384) return false;                       // LBO field: 14 bits of 16-byte units
     if (p.gin.guard + (long long)p.n_groups * C::TPS * kTileM + p.gin.halo > p.gin.Lp) return false;
     const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
-    p.w_bytes = C::BLOCKS * C::NCOLS * 32;
+    p.w_bytes = C::BLOCKS * C::BLOCK_N * 32;
     // ring depth: as deep as fits, up to 2 strips (whole-K stages) or 4 (k-chunked stages)
     const int target = C::NKC > 1 ? kMaxStage : 2;
     for (p.n_stage = target; p.n_stage >= 1; p.n_stage--)
         if (plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>()).total <= (uint32_t)kSmemLimit) break;
-    if (p.n_stage < 1) return false;
+    if (p.n_stage < min_stage) return false;
     const SmemPlan sp = plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>());
     err = cudaFuncSetAttribute(shiftgemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
     if (err != cudaSuccess) return true;

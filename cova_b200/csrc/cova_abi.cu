@@ -58,6 +58,16 @@ extern "C" const char *cova_strerror(int code) {
         default: return "unknown error";
     }
 }
+extern "C" int cova_host_alloc(void **out, size_t bytes) {
+    if (!out || !bytes) return set_err(COVA_E_INVAL, "null argument");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(e == cudaErrorMemoryAllocation ? COVA_E_NOMEM : COVA_E_NODEVICE, "cudaMallocHost: %s", cudaGetErrorString(e)); }
+    return COVA_OK;
+}
+extern "C" void cova_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
 extern "C" int cova_device_count(int *n) {
     if (!n) return set_err(COVA_E_INVAL, "null argument");
     int c = 0;
@@ -198,16 +208,17 @@ static void ccl_free(CclBuffers &b, bool own_masks) {
     if (b.d_stats) cudaFree(b.d_stats);
     if (b.d_nlabels) cudaFree(b.d_nlabels);
 }
-static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_threshold, bool want_labels, cudaStream_t st) {
+static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_threshold, bool want_labels, cudaStream_t st,
+                      size_t first = 0, bool reset_cursor = true) {
     if (n <= 0) return COVA_OK;
     CclArgs a;
-    a.masks = d_masks; a.H = b.H; a.W = b.W; a.nbx = b.nbx; a.nby = b.nby;
+    a.masks = d_masks + first * (size_t)b.H * b.W; a.H = b.H; a.W = b.W; a.nbx = b.nbx; a.nby = b.nby;
     a.area_thresh = (int)cc_threshold;   // `settings.cc_threshold as i32` (imp.rs:248)
-    a.blob = b.d_blob; a.blob_cap = b.blob_cap; a.cursor = b.d_cursor; a.offsets = b.d_offsets; a.lens = b.d_lens;
+    a.blob = b.d_blob; a.blob_cap = b.blob_cap; a.cursor = b.d_cursor; a.offsets = b.d_offsets + first; a.lens = b.d_lens + first;
     a.labels = want_labels ? b.d_labels : nullptr;
     a.stats = want_labels ? b.d_stats : nullptr;
     a.n_labels = want_labels ? b.d_nlabels : nullptr;
-    COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
+    if (reset_cursor) COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
     ccl_bbox_kernel<<<n, b.threads, b.smem, st>>>(a);
     COVA_CUDA(cudaGetLastError());
     return COVA_OK;
@@ -317,9 +328,28 @@ struct cova_pipeline {
     uint8_t *d_frames = nullptr;
     int *d_newest = nullptr;
     uint32_t cur_streams = 0, cur_fps = 0, cur_windows = 0, table_streams = 0, table_fps = 0;
+    // A batch is processed in chunks of whole chains: the activation buffers are sized for ONE chunk, and
+    // process_host() overlaps the H2D copy of chunk c+1, the kernels of chunk c and the D2H of chunk c-1.
+    uint32_t chunk_streams = 0;          // chains per chunk (capacity)
+    uint32_t ck_stream0 = 0, ck_n_streams = 0, ck_window0 = 0, ck_windows = 0;   // chunk being processed
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    // Two batch slots (frame pool + box arena + events) so that submit_host(k+1) can copy in while batch k computes
+    // and batch k-1's boxes copy out.  The synchronous entry points use slot 0.
+    struct Slot {
+        uint8_t *d_frames = nullptr;
+        CclBuffers ccl;
+        std::vector<cudaEvent_t> ev_in, ev_done;
+        unsigned long long *h_cursor = nullptr;      // pinned: per-chunk cursor snapshots (2 words each)
+        uint32_t n_streams = 0, fps = 0, n_windows = 0;
+        bool busy = false;
+    } slot[2];
+    int cur_slot = 0, next_submit = 0, next_collect = 0;
     int sizes_h[5], sizes_w[5];          // extents: [0] input, [1..4] encoder outputs
     Geom gx[4];                          // X0..X3 (Tn = 4): inputs of enc1..enc4
     Geom gd[4];                          // D0in..D3in (Tn = 1): inputs of dec0..dec3
+    Geom gx0f, gp1;                      // per-FRAME first-conv input (x-pair packed) and pooled output (Tn = 1, N = frames)
+    uint4 *x0f = nullptr, *p1 = nullptr;
+    std::vector<int> h_newest;
     uint4 *x[4] = {nullptr, nullptr, nullptr, nullptr};
     uint4 *d[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t *d_mask = nullptr, *d_stacked = nullptr;
@@ -399,7 +429,28 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_err(COVA_E_CUDA, "stream creation failed"));
     p->stream = p->own_stream;
 
-    const int N = (int)p->max_windows;
+    {   // chunking: ~1024 windows per chunk, at most 16 chunks; tiny pipelines stay single-chunk
+        const uint32_t wps = windows_per_stream(max_fps, timestep, gamma);
+        uint32_t chunks = std::min<uint32_t>(16, std::max<uint32_t>(1, p->max_windows / 1024));
+        const uint32_t hint = (flags >> 16) & 0xffu;
+        if (hint) chunks = hint;
+        chunks = std::min(chunks, max_streams);
+        p->chunk_streams = (max_streams + chunks - 1) / chunks;
+        chunks = (max_streams + p->chunk_streams - 1) / p->chunk_streams;
+        if (cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(set_err(COVA_E_CUDA, "stream creation failed"));
+        for (auto &sl : p->slot) {
+            sl.ev_in.resize(chunks); sl.ev_done.resize(chunks);
+            for (uint32_t c = 0; c < chunks; c++)
+                if (cudaEventCreateWithFlags(&sl.ev_in[c], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&sl.ev_done[c], cudaEventDisableTiming) != cudaSuccess)
+                    return fail(set_err(COVA_E_CUDA, "event creation failed"));
+        }
+        (void)wps;
+    }
+    const int N = (int)(p->chunk_streams * windows_per_stream(max_fps, timestep, gamma));   // windows per chunk
+    const int NB = (int)p->max_windows;                                                       // windows per batch
     p->sizes_h[0] = (int)h_mb; p->sizes_w[0] = (int)w_mb;
     for (int i = 1; i <= 4; i++) { p->sizes_h[i] = (p->sizes_h[i - 1] + 1) / 2; p->sizes_w[i] = (p->sizes_w[i - 1] + 1) / 2; }
     // encoder inputs (Tn = 4): X0 (8 ch incl. padding), X1 (16), X2 (32), X3 (64)
@@ -414,22 +465,34 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
         return COVA_OK;
     };
     for (int i = 0; i < 4; i++) {
-        if ((rc = alloc_zero(&p->x[i], p->gx[i]))) return fail(rc);
+        // X0 in window layout is only consumed by the validation kernels; the tcgen05 path works per frame
+        if (i > 0 || p->impl == COVA_IMPL_SIMT)
+            if ((rc = alloc_zero(&p->x[i], p->gx[i]))) return fail(rc);
         if ((rc = alloc_zero(&p->d[i], p->gd[i]))) return fail(rc);
     }
+    const int F = (int)(p->chunk_streams * max_fps);
+    p->gx0f = make_geom(p->sizes_h[0], p->sizes_w[0], 8, 1, F);
+    p->gp1 = make_geom(p->sizes_h[1], p->sizes_w[1], kEncCout[0], 1, F);
+    if ((rc = alloc_zero(&p->x0f, p->gx0f))) return fail(rc);
+    if ((rc = alloc_zero(&p->p1, p->gp1))) return fail(rc);
     p->frame_bytes = (size_t)w_mb * h_mb * 4;
-    cudaError_t e = cudaMalloc(&p->d_frames, p->frame_bytes * max_streams * max_fps);
+    cudaError_t e = cudaMalloc(&p->slot[0].d_frames, p->frame_bytes * max_streams * max_fps);
+    p->d_frames = p->slot[0].d_frames;
     if (e == cudaSuccess) e = cudaMalloc(&p->d_newest, sizeof(int) * std::max(1, N));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_mask, (size_t)std::max(1, N) * w_mb * h_mb);
-    if (e == cudaSuccess) e = cudaMemset(p->d_mask, 0, (size_t)std::max(1, N) * w_mb * h_mb);
-    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_LOGITS)) e = cudaMalloc(&p->d_logits, sizeof(float) * (size_t)N * w_mb * h_mb);
-    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_STACKED)) e = cudaMalloc(&p->d_stacked, p->frame_bytes * timestep * (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_mask, (size_t)std::max(1, NB) * w_mb * h_mb);
+    if (e == cudaSuccess) e = cudaMemset(p->d_mask, 0, (size_t)std::max(1, NB) * w_mb * h_mb);
+    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_LOGITS)) e = cudaMalloc(&p->d_logits, sizeof(float) * (size_t)NB * w_mb * h_mb);
+    if (e == cudaSuccess && (flags & COVA_FLAG_KEEP_STACKED)) e = cudaMalloc(&p->d_stacked, p->frame_bytes * timestep * (size_t)NB);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_watchdog, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(p->d_watchdog, 0, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMallocHost(&p->h_pinned, sizeof(unsigned long long) * (2 + 2 * (size_t)std::max(1, N)));
+    if (e == cudaSuccess) e = cudaMallocHost(&p->h_pinned, sizeof(unsigned long long) * (2 + 2 * (size_t)std::max(1, NB) + 2 * 64));
     if (e != cudaSuccess) return fail(set_err(COVA_E_CUDA, "pipeline allocation: %s", cudaGetErrorString(e)));
-    p->ccl.d_masks = p->d_mask;
-    if ((rc = ccl_alloc(p->ccl, (int)h_mb, (int)w_mb, std::max(1, N), false))) return fail(rc);
+    p->slot[0].ccl.d_masks = p->d_mask;
+    if ((rc = ccl_alloc(p->slot[0].ccl, (int)h_mb, (int)w_mb, std::max(1, NB), false))) return fail(rc);
+    p->ccl = p->slot[0].ccl;
+    if (cudaMallocHost(&p->slot[0].h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess ||
+        cudaMallocHost(&p->slot[1].h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess)
+        return fail(set_err(COVA_E_CUDA, "pinned allocation failed"));
 
     // weights: raw fp32 for the validation kernels, packed fp16 operand blocks for the tcgen05 path
     if ((rc = dev_upload(&p->d_wraw, p->hw.storage.data(), p->hw.storage.size() * sizeof(float)))) return fail(rc);
@@ -454,13 +517,21 @@ extern "C" void cova_pipeline_free(cova_pipeline *p) {
     cudaDeviceSynchronize();
     for (int i = 0; i < 4; i++) {
         if (p->x[i]) cudaFree(p->x[i]);
+        if (i == 0 && p->x0f) cudaFree(p->x0f);
+        if (i == 0 && p->p1) cudaFree(p->p1);
         if (p->d[i]) cudaFree(p->d[i]);
         if (p->enc[i].wpack) cudaFree(p->enc[i].wpack);
         if (p->enc[i].epi) cudaFree(p->enc[i].epi);
         if (p->dec[i].wpack) cudaFree(p->dec[i].wpack);
         if (p->dec[i].epi) cudaFree(p->dec[i].epi);
     }
-    if (p->d_frames) cudaFree(p->d_frames);
+    for (auto &sl : p->slot) {
+        if (sl.d_frames) cudaFree(sl.d_frames);
+        ccl_free(sl.ccl, false);
+        if (sl.h_cursor) cudaFreeHost(sl.h_cursor);
+        for (auto e : sl.ev_in) cudaEventDestroy(e);
+        for (auto e : sl.ev_done) cudaEventDestroy(e);
+    }
     if (p->d_newest) cudaFree(p->d_newest);
     if (p->d_mask) cudaFree(p->d_mask);
     if (p->d_logits) cudaFree(p->d_logits);
@@ -468,8 +539,9 @@ extern "C" void cova_pipeline_free(cova_pipeline *p) {
     if (p->d_wraw) cudaFree(p->d_wraw);
     if (p->d_watchdog) cudaFree(p->d_watchdog);
     if (p->h_pinned) cudaFreeHost(p->h_pinned);
-    ccl_free(p->ccl, false);
     for (auto e : p->events) cudaEventDestroy(e);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     cudaGetLastError();
     delete p;
@@ -497,16 +569,34 @@ static int set_batch_shape(cova_pipeline *p, uint32_t n_streams, uint32_t fps) {
     const uint32_t wps = windows_per_stream(fps, p->T, p->gamma);
     if (n_streams * wps > p->max_windows) return set_err(COVA_E_INVAL, "batch produces more windows than the pipeline was sized for");
     p->cur_streams = n_streams; p->cur_fps = fps; p->cur_windows = n_streams * wps;
-    if (p->table_streams != n_streams || p->table_fps != fps) {
-        std::vector<int> newest(std::max<size_t>(1, p->cur_windows));
+    const uint32_t tstreams = std::min(n_streams, p->chunk_streams);
+    if (p->table_streams != tstreams || p->table_fps != fps) {
+        // chunk-relative table: window k of a chunk -> index (inside the chunk's frames) of its newest frame
+        std::vector<int> &newest = p->h_newest;
+        newest.assign(std::max<size_t>(1, (size_t)tstreams * wps), 0);
         size_t k = 0;
-        for (uint32_t s = 0; s < n_streams; s++)
+        for (uint32_t s = 0; s < tstreams; s++)
             for (uint32_t w = 0; w < wps; w++) newest[k++] = (int)(s * fps + (p->T - 1) + w * p->gamma);
-        if (p->cur_windows)
-            COVA_CUDA(cudaMemcpyAsync(p->d_newest, newest.data(), sizeof(int) * p->cur_windows, cudaMemcpyHostToDevice, p->stream));
-        COVA_CUDA(cudaStreamSynchronize(p->stream));   // `newest` is a stack temporary
-        p->table_streams = n_streams; p->table_fps = fps;
+        if (k) COVA_CUDA(cudaMemcpyAsync(p->d_newest, newest.data(), sizeof(int) * k, cudaMemcpyHostToDevice, p->stream));
+        COVA_CUDA(cudaStreamSynchronize(p->stream));
+        p->table_streams = tstreams; p->table_fps = fps;
     }
+    return COVA_OK;
+}
+
+static void use_slot(cova_pipeline *p, int k);
+static uint32_t n_chunks_of(const cova_pipeline *p) { return (p->cur_streams + p->chunk_streams - 1) / p->chunk_streams; }
+static void select_chunk(cova_pipeline *p, uint32_t c) {
+    const uint32_t wps = windows_per_stream(p->cur_fps, p->T, p->gamma);
+    p->ck_stream0 = c * p->chunk_streams;
+    p->ck_n_streams = std::min(p->chunk_streams, p->cur_streams - p->ck_stream0);
+    p->ck_window0 = p->ck_stream0 * wps;
+    p->ck_windows = p->ck_n_streams * wps;
+}
+static int require_single_chunk(cova_pipeline *p) {
+    if (p->cur_streams > p->chunk_streams)
+        return set_err(COVA_E_UNSUPPORTED, "stage-wise calls need a batch that fits one chunk; use cova_pipeline_run / process_host");
+    select_chunk(p, 0);
     return COVA_OK;
 }
 
@@ -515,6 +605,7 @@ extern "C" int cova_pipeline_load_frames(cova_pipeline *p, const uint8_t *frames
     COVA_CUDA(cudaSetDevice(p->device));
     int rc = set_batch_shape(p, n_streams, fps);
     if (rc) return rc;
+    use_slot(p, 0);
     COVA_CUDA(cudaMemcpyAsync(p->d_frames, frames, p->frame_bytes * n_streams * fps,
                               is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
     return COVA_OK;
@@ -524,8 +615,51 @@ extern "C" int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, 
     if (!p || !masks) return set_err(COVA_E_INVAL, "null argument");
     if (!n || n > p->max_windows) return set_err(COVA_E_INVAL, "mask batch exceeds the pipeline's window capacity");
     COVA_CUDA(cudaSetDevice(p->device));
-    p->cur_windows = n;
+    p->cur_windows = n; p->cur_streams = 0;
+    use_slot(p, 0);
     COVA_CUDA(cudaMemcpyAsync(p->d_mask, masks, (size_t)n * p->W * p->H, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, p->stream));
+    return COVA_OK;
+}
+
+static int tensorise_chunk(cova_pipeline *p) {
+    const int N = (int)p->ck_windows;
+    if (!N) return COVA_OK;
+    const uint8_t *frames = p->d_frames + (size_t)p->ck_stream0 * p->cur_fps * p->frame_bytes;
+    if (p->d_stacked) {
+        const size_t S = p->frame_bytes;
+        uint8_t *dst = p->d_stacked + (size_t)p->ck_window0 * p->T * S;
+        if (S % 16 == 0) {
+            long long total = (long long)N * p->T * (S / 16);
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            stack_rgba_kernel<uint4><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint4 *>(frames), p->d_newest,
+                                                                   reinterpret_cast<uint4 *>(dst), (int)(S / 16), (int)p->T, total);
+        } else {
+            long long total = (long long)N * p->T * (S / 4);
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            stack_rgba_kernel<uint32_t><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(frames), p->d_newest,
+                                                                      reinterpret_cast<uint32_t *>(dst), (int)(S / 4), (int)p->T, total);
+        }
+        COVA_CUDA(cudaGetLastError());
+        p->launches++;
+        prof_mark(p, "stack_rgba");
+    }
+    {   // per-frame first-conv input (tcgen05 path)
+        const int F = (int)(p->ck_n_streams * p->cur_fps);
+        long long total = (long long)F * p->H * p->gx0f.Wh;
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
+        tensorise_frames_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F);
+        COVA_CUDA(cudaGetLastError());
+        p->launches++;
+        prof_mark(p, "tensorise_frames");
+    }
+    if (p->x[0]) {   // window-layout input of the validation kernels
+        long long total = (long long)N * p->H * p->gx[0].Wh * kT;
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
+        tensorise_x0_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(frames), p->d_newest, p->x[0], p->gx[0], N);
+        COVA_CUDA(cudaGetLastError());
+        p->launches++;
+        prof_mark(p, "tensorise_x0");
+    }
     return COVA_OK;
 }
 
@@ -533,31 +667,8 @@ extern "C" int cova_pipeline_tensorise(cova_pipeline *p) {
     if (!p) return set_err(COVA_E_INVAL, "null handle");
     if (!p->cur_windows) return COVA_OK;
     COVA_CUDA(cudaSetDevice(p->device));
-    const int N = (int)p->cur_windows;
-    if (p->d_stacked) {
-        const size_t S = p->frame_bytes;
-        if (S % 16 == 0) {
-            long long total = (long long)N * p->T * (S / 16);
-            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
-            stack_rgba_kernel<uint4><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint4 *>(p->d_frames), p->d_newest,
-                                                                   reinterpret_cast<uint4 *>(p->d_stacked), (int)(S / 16), (int)p->T, total);
-        } else {
-            long long total = (long long)N * p->T * (S / 4);
-            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
-            stack_rgba_kernel<uint32_t><<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(p->d_frames), p->d_newest,
-                                                                      reinterpret_cast<uint32_t *>(p->d_stacked), (int)(S / 4), (int)p->T, total);
-        }
-        COVA_CUDA(cudaGetLastError());
-        p->launches++;
-        prof_mark(p, "stack_rgba");
-    }
-    long long total = (long long)N * p->H * p->gx[0].Wh * kT;
-    int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
-    tensorise_x0_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(p->d_frames), p->d_newest, p->x[0], p->gx[0], N);
-    COVA_CUDA(cudaGetLastError());
-    p->launches++;
-    prof_mark(p, "tensorise_x0");
-    return COVA_OK;
+    int rc = require_single_chunk(p);
+    return rc ? rc : tensorise_chunk(p);
 }
 
 // ---- layer launchers -------------------------------------------------------------------------------
@@ -567,8 +678,9 @@ static void crop_for(int in_extent, int target, int &crop_lo) {
 }
 
 static int simt_layer(cova_pipeline *p, int layer) {
-    const int N = (int)p->cur_windows;
+    const int N = (int)p->ck_windows;
     const float *w = p->d_wraw;
+    if (layer == 0 && !p->x[0]) return set_err(COVA_E_UNSUPPORTED, "validation kernel of layer 0 needs a pipeline created with COVA_IMPL_SIMT");
     if (layer < 4) {
         const int i = layer;
         SimtEncArgs a;
@@ -598,7 +710,8 @@ static int simt_layer(cova_pipeline *p, int layer) {
     a.w = w + p->hw.off_dec[i][0]; a.b = w + p->hw.off_dec[i][1];
     a.gamma = w + p->hw.off_dec[i][2]; a.beta = w + p->hw.off_dec[i][3]; a.mean = w + p->hw.off_dec[i][4]; a.var = w + p->hw.off_dec[i][5];
     a.head_w = w + p->hw.off_head[0]; a.head_b = w + p->hw.off_head[1];
-    a.mask = p->d_mask; a.logits = p->d_logits;
+    a.mask = p->d_mask + (size_t)p->ck_window0 * p->W * p->H;
+    a.logits = p->d_logits ? p->d_logits + (size_t)p->ck_window0 * p->W * p->H : nullptr;
     a.Cin = kDecCin[i]; a.Cout = kDecCout[i]; a.N = N;
     a.Ht = p->sizes_h[3 - i]; a.Wt = p->sizes_w[3 - i];
     crop_for(a.gin.H, a.Ht, a.crop_t);
@@ -616,20 +729,29 @@ static int simt_layer(cova_pipeline *p, int layer) {
     return COVA_OK;
 }
 
+// Candidate tile configurations in order of preference; a configuration that can double-buffer its strips
+// (ring depth >= 2) beats an earlier one that cannot.
 template <class C0, class... Cs>
-static int launch_first_fit(const tc::LayerParams &lp, int n_sms, cudaStream_t st) {
+static int launch_fit(const tc::LayerParams &lp, int n_sms, cudaStream_t st, int min_stage) {
     cudaError_t err = cudaSuccess;
-    if (tc::try_launch<C0>(lp, n_sms, st, err)) {
+    if (tc::try_launch<C0>(lp, n_sms, st, err, min_stage)) {
         if (err != cudaSuccess) return set_err(COVA_E_CUDA, "tcgen05 layer launch: %s", cudaGetErrorString(err));
         return COVA_OK;
     }
-    if constexpr (sizeof...(Cs) > 0) return launch_first_fit<Cs...>(lp, n_sms, st);
-    else return set_err(COVA_E_UNSUPPORTED, "no tcgen05 tile configuration fits shared memory for this macroblock grid");
+    if constexpr (sizeof...(Cs) > 0) return launch_fit<Cs...>(lp, n_sms, st, min_stage);
+    else return COVA_E_UNSUPPORTED;
+}
+template <class... Cs>
+static int launch_first_fit(const tc::LayerParams &lp, int n_sms, cudaStream_t st) {
+    int rc = launch_fit<Cs...>(lp, n_sms, st, 2);
+    if (rc == COVA_E_UNSUPPORTED) rc = launch_fit<Cs...>(lp, n_sms, st, 1);
+    if (rc == COVA_E_UNSUPPORTED) return set_err(COVA_E_UNSUPPORTED, "no tcgen05 tile configuration fits shared memory for this macroblock grid");
+    return rc;
 }
 
 static int tc_layer(cova_pipeline *p, int layer) {
     using namespace tc;
-    const int N = (int)p->cur_windows;
+    const int N = (int)p->ck_windows;
     LayerParams lp;
     memset(&lp, 0, sizeof(lp));
     lp.N = N; lp.watchdog = p->d_watchdog; lp.dbg = p->dbg;
@@ -649,13 +771,34 @@ static int tc_layer(cova_pipeline *p, int layer) {
         for (int c = 0; c < kEncCout[i]; c++)
             if (!(p->hw.enc[i].gamma[c] >= 0.f)) lp.bn_nonneg = 0;
         //                                  MODE   CIN_CB NCOLS TPS KCH COUT
-        if (i == 0) rc = launch_first_fit<Cfg<MODE_ENC, 1, 16, 4, 1, 16>, Cfg<MODE_ENC, 1, 16, 2, 1, 16>, Cfg<MODE_ENC, 1, 16, 1, 1, 16>>(lp, p->n_sms, p->stream);
-        else if (i == 1) rc = launch_first_fit<Cfg<MODE_ENC, 2, 32, 4, 2, 32>, Cfg<MODE_ENC, 2, 32, 2, 2, 32>, Cfg<MODE_ENC, 2, 32, 1, 2, 32>>(lp, p->n_sms, p->stream);
+        if (i == 0) {
+            // first block: conv+ReLU+BN+pool once per FRAME, then PointWiseTN gathers the 4 frames of every window
+            const int F = (int)(p->ck_n_streams * p->cur_fps);
+            lp.in = p->x0f; lp.gin = p->gx0f; lp.out = p->p1; lp.gout = p->gp1; lp.out2 = nullptr; lp.N = F;
+            rc = launch_first_fit<Cfg<MODE_ENCF, 1, 16, 8, 1, 16>, Cfg<MODE_ENCF, 1, 16, 4, 1, 16>, Cfg<MODE_ENCF, 1, 16, 2, 1, 16>,
+                                  Cfg<MODE_ENCF, 1, 16, 1, 1, 16>>(lp, p->n_sms, p->stream);
+            if (rc) return rc;
+            p->launches++;
+            prof_mark(p, "tc_enc1_conv");
+            TnArgs ta;
+            ta.p1 = p->p1; ta.gp1 = p->gp1; ta.x1 = p->x[1]; ta.gx1 = p->gx[1]; ta.skip = p->d[3]; ta.gskip = p->gd[3];
+            ta.skip_cb = kDecCout[2] / 8; ta.newest = p->d_newest; ta.n_windows = N; ta.CB = kEncCout[0] / 8;
+            memcpy(ta.w1, p->hw.enc[0].tn_w1, 64);
+            memcpy(ta.w2, p->hw.enc[0].tn_w2, 64);
+            long long total = (long long)ta.CB * 4 * N * p->gx[1].S;
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            pointwise_tn_kernel<<<blocks, 256, 0, p->stream>>>(ta);
+            COVA_CUDA(cudaGetLastError());
+            p->launches++;
+            prof_mark(p, "enc1_pointwise_tn");
+            return COVA_OK;
+        }
+        if (i == 1) rc = launch_first_fit<Cfg<MODE_ENC, 2, 32, 4, 2, 32>, Cfg<MODE_ENC, 2, 32, 2, 2, 32>, Cfg<MODE_ENC, 2, 32, 1, 2, 32>>(lp, p->n_sms, p->stream);
         else if (i == 2) rc = launch_first_fit<Cfg<MODE_ENC, 4, 64, 2, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 2, 64>>(lp, p->n_sms, p->stream);
         else rc = launch_first_fit<Cfg<MODE_ENC, 8, 128, 1, 2, 128>>(lp, p->n_sms, p->stream);
         if (rc) return rc;
         p->launches++;
-        prof_mark(p, i == 0 ? "tc_enc1" : i == 1 ? "tc_enc2" : i == 2 ? "tc_enc3" : "tc_enc4");
+        prof_mark(p, i == 1 ? "tc_enc2" : i == 2 ? "tc_enc3" : "tc_enc4");
         return COVA_OK;
     }
     const int i = layer - 4;
@@ -667,7 +810,8 @@ static int tc_layer(cova_pipeline *p, int layer) {
     lp.Ht = p->sizes_h[3 - i]; lp.Wt = p->sizes_w[3 - i];
     crop_for(lp.gin.H, lp.Ht, lp.crop_t);
     crop_for(lp.gin.W, lp.Wt, lp.crop_l);
-    lp.mask = p->d_mask; lp.logits = p->d_logits;
+    lp.mask = p->d_mask + (size_t)p->ck_window0 * p->W * p->H;
+    lp.logits = p->d_logits ? p->d_logits + (size_t)p->ck_window0 * p->W * p->H : nullptr;
     if (i == 0) rc = launch_first_fit<Cfg<MODE_DEC, 16, 128, 1, 2, 64>>(lp, p->n_sms, p->stream);
     else if (i == 1) rc = launch_first_fit<Cfg<MODE_DEC, 16, 128, 1, 2, 32>>(lp, p->n_sms, p->stream);
     else if (i == 2) rc = launch_first_fit<Cfg<MODE_DEC, 8, 64, 1, 4, 16>, Cfg<MODE_DEC, 8, 64, 1, 2, 16>>(lp, p->n_sms, p->stream);
@@ -683,16 +827,34 @@ extern "C" int cova_pipeline_run_layer(cova_pipeline *p, int layer, uint32_t imp
     if (layer < 0 || layer > 7 || impl > COVA_IMPL_SIMT) return set_err(COVA_E_INVAL, "layer must be 0..7, impl 0 or 1");
     if (!p->cur_windows) return COVA_OK;
     COVA_CUDA(cudaSetDevice(p->device));
+    int rc = require_single_chunk(p);
+    if (rc) return rc;
     return impl == COVA_IMPL_SIMT ? simt_layer(p, layer) : tc_layer(p, layer);
+}
+
+static int blobnet_chunk(cova_pipeline *p) {
+    if (!p->ck_windows) return COVA_OK;
+    for (int layer = 0; layer < 8; layer++) {
+        int rc = p->impl == COVA_IMPL_SIMT ? simt_layer(p, layer) : tc_layer(p, layer);
+        if (rc) return rc;
+    }
+    return COVA_OK;
 }
 
 extern "C" int cova_pipeline_blobnet(cova_pipeline *p) {
     if (!p) return set_err(COVA_E_INVAL, "null handle");
     if (!p->cur_windows) return COVA_OK;
     COVA_CUDA(cudaSetDevice(p->device));
-    for (int layer = 0; layer < 8; layer++) {
-        int rc = p->impl == COVA_IMPL_SIMT ? simt_layer(p, layer) : tc_layer(p, layer);
-        if (rc) return rc;
+    int rc = require_single_chunk(p);
+    return rc ? rc : blobnet_chunk(p);
+}
+
+static int ccl_range(cova_pipeline *p, size_t first, int n, bool reset_cursor) {
+    int rc = ccl_launch(p->ccl, p->d_mask, n, p->cc_threshold, false, p->stream, first, reset_cursor);
+    if (rc) return rc;
+    if (n > 0) {
+        p->launches++;
+        prof_mark(p, "ccl_bbox");
     }
     return COVA_OK;
 }
@@ -704,11 +866,7 @@ extern "C" int cova_pipeline_ccl(cova_pipeline *p) {
         COVA_CUDA(cudaMemsetAsync(p->ccl.d_cursor, 0, 2 * sizeof(unsigned long long), p->stream));
         return COVA_OK;
     }
-    int rc = ccl_launch(p->ccl, p->d_mask, (int)p->cur_windows, p->cc_threshold, false, p->stream);
-    if (rc) return rc;
-    p->launches++;
-    prof_mark(p, "ccl_bbox");
-    return COVA_OK;
+    return ccl_range(p, 0, (int)p->cur_windows, true);
 }
 
 static void prof_begin(cova_pipeline *p) {
@@ -718,19 +876,34 @@ static void prof_begin(cova_pipeline *p) {
     prof_mark(p, "start");
 }
 
-extern "C" int cova_pipeline_run(cova_pipeline *p) {
-    if (!p) return set_err(COVA_E_INVAL, "null handle");
-    prof_begin(p);
-    int rc = cova_pipeline_tensorise(p);
-    if (!rc) rc = cova_pipeline_blobnet(p);
-    if (!rc) rc = cova_pipeline_ccl(p);
+// all kernels of one chunk, on p->stream
+static int run_chunk(cova_pipeline *p, uint32_t c) {
+    select_chunk(p, c);
+    int rc = tensorise_chunk(p);
+    if (!rc) rc = blobnet_chunk(p);
+    if (!rc) rc = ccl_range(p, p->ck_window0, (int)p->ck_windows, c == 0);
     return rc;
 }
 
-extern "C" int cova_pipeline_sync(cova_pipeline *p) {
+extern "C" int cova_pipeline_run(cova_pipeline *p) {
     if (!p) return set_err(COVA_E_INVAL, "null handle");
     COVA_CUDA(cudaSetDevice(p->device));
-    cudaError_t e = cudaStreamSynchronize(p->stream);
+    prof_begin(p);
+    if (!p->cur_streams) return cova_pipeline_ccl(p);      // masks were loaded directly
+    if (!p->cur_windows) {
+        COVA_CUDA(cudaMemsetAsync(p->ccl.d_cursor, 0, 2 * sizeof(unsigned long long), p->stream));
+        return COVA_OK;
+    }
+    const uint32_t nc = n_chunks_of(p);
+    for (uint32_t c = 0; c < nc; c++) {
+        int rc = run_chunk(p, c);
+        if (rc) return rc;
+    }
+    return COVA_OK;
+}
+
+static int sync_stream(cova_pipeline *p, cudaStream_t st) {
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         unsigned int code = 0;
         cudaMemcpy(&code, p->d_watchdog, sizeof(code), cudaMemcpyDeviceToHost);
@@ -738,14 +911,26 @@ extern "C" int cova_pipeline_sync(cova_pipeline *p) {
         snprintf(extra, sizeof(extra), " (barrier watchdog code %u)", code);
         return set_err(COVA_E_CUDA, "stream synchronize: %s%s", cudaGetErrorString(e), extra);
     }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_sync(cova_pipeline *p) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    COVA_CUDA(cudaSetDevice(p->device));
+    int rc = sync_stream(p, p->stream);
+    if (rc) return rc;
     if (p->profiling && p->ev_used > 1) {
+        // per-kernel device time, summed over the chunks of the batch
         p->last_ms.clear();
         p->last_names.clear();
         for (size_t i = 1; i < p->ev_used; i++) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, p->events[i - 1], p->events[i]);
-            p->last_ms.push_back(ms);
-            p->last_names.push_back(p->names[i]);
+            size_t k = 0;
+            for (; k < p->last_names.size(); k++)
+                if (p->last_names[k] == p->names[i]) break;
+            if (k == p->last_names.size()) { p->last_names.push_back(p->names[i]); p->last_ms.push_back(0.f); }
+            p->last_ms[k] += ms;
         }
         p->ev_used = 0;
         p->names.clear();
@@ -777,12 +962,100 @@ extern "C" int cova_pipeline_fetch_boxes(cova_pipeline *p, uint8_t *blob, size_t
     return COVA_OK;
 }
 
+static void use_slot(cova_pipeline *p, int k) {
+    p->cur_slot = k;
+    p->d_frames = p->slot[k].d_frames;
+    p->ccl = p->slot[k].ccl;
+}
+static int ensure_slot1(cova_pipeline *p) {
+    auto &sl = p->slot[1];
+    if (sl.d_frames) return COVA_OK;
+    COVA_CUDA(cudaMalloc(&sl.d_frames, p->frame_bytes * p->max_streams * p->max_fps));
+    sl.ccl.d_masks = p->d_mask;
+    return ccl_alloc(sl.ccl, (int)p->H, (int)p->W, std::max<int>(1, (int)p->max_windows), false);
+}
+
+// Host frames in, boxes out, asynchronously.  Three streams: the H2D copy of chunk c+1, the kernels of chunk c and
+// the D2H copy of earlier boxes overlap; with two batches in flight (submit k+1 before collect k) the copies of
+// one batch hide behind the kernels of the other.  A chunk's boxes occupy one contiguous range of the slot's device
+// arena (the cursor is only reset at the start of a batch), so each chunk needs exactly one blob copy of exactly
+// the bytes it produced.
+extern "C" int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps) {
+    if (!p || !frames) return set_err(COVA_E_INVAL, "null argument");
+    COVA_CUDA(cudaSetDevice(p->device));
+    const int k = p->next_submit;
+    if (p->slot[k].busy) return set_err(COVA_E_INVAL, "two batches are already in flight: collect one first");
+    int rc = k == 1 ? ensure_slot1(p) : COVA_OK;
+    if (rc) return rc;
+    if ((rc = set_batch_shape(p, n_streams, fps))) return rc;
+    use_slot(p, k);
+    auto &sl = p->slot[k];
+    sl.n_streams = n_streams; sl.fps = fps; sl.n_windows = p->cur_windows; sl.busy = true;
+    p->next_submit = k ^ 1;
+    if (!p->cur_windows) return COVA_OK;
+    const uint32_t nc = n_chunks_of(p);
+    const size_t chain_bytes = p->frame_bytes * fps;
+    for (uint32_t c = 0; c < nc; c++) {
+        const size_t s0 = (size_t)c * p->chunk_streams, ns = std::min<size_t>(p->chunk_streams, n_streams - s0);
+        COVA_CUDA(cudaMemcpyAsync(sl.d_frames + s0 * chain_bytes, frames + s0 * chain_bytes, ns * chain_bytes, cudaMemcpyHostToDevice, p->s_in));
+        COVA_CUDA(cudaEventRecord(sl.ev_in[c], p->s_in));
+    }
+    for (uint32_t c = 0; c < nc; c++) {
+        COVA_CUDA(cudaStreamWaitEvent(p->stream, sl.ev_in[c], 0));
+        if ((rc = run_chunk(p, c))) return rc;
+        COVA_CUDA(cudaMemcpyAsync(sl.h_cursor + 2 * c, sl.ccl.d_cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+        COVA_CUDA(cudaEventRecord(sl.ev_done[c], p->stream));
+    }
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                                          uint64_t *lens, uint32_t *n_windows) {
+    if (!p || !blob_len) return set_err(COVA_E_INVAL, "null argument");
+    COVA_CUDA(cudaSetDevice(p->device));
+    const int k = p->next_collect;
+    auto &sl = p->slot[k];
+    if (!sl.busy) return set_err(COVA_E_INVAL, "no batch in flight");
+    sl.busy = false;
+    p->next_collect = k ^ 1;
+    if (n_windows) *n_windows = sl.n_windows;
+    *blob_len = 0;
+    if (!sl.n_windows) return COVA_OK;
+    const uint32_t wps = windows_per_stream(sl.fps, p->T, p->gamma);
+    const uint32_t nc = (sl.n_streams + p->chunk_streams - 1) / p->chunk_streams;
+    unsigned long long prev = 0;
+    bool too_small = false;
+    for (uint32_t c = 0; c < nc; c++) {
+        if (cudaEventSynchronize(sl.ev_done[c]) != cudaSuccess) return sync_stream(p, p->stream);
+        if (sl.h_cursor[2 * c + 1]) return set_err(COVA_E_CUDA, "device box arena overflow (internal sizing error)");
+        const unsigned long long end = sl.h_cursor[2 * c];
+        const size_t w0 = (size_t)c * p->chunk_streams * wps;
+        const size_t nw = (size_t)std::min<uint32_t>(p->chunk_streams, sl.n_streams - c * p->chunk_streams) * wps;
+        if (offsets) COVA_CUDA(cudaMemcpyAsync(offsets + w0, sl.ccl.d_offsets + w0, nw * sizeof(uint64_t), cudaMemcpyDeviceToHost, p->s_out));
+        if (lens) COVA_CUDA(cudaMemcpyAsync(lens + w0, sl.ccl.d_lens + w0, nw * sizeof(uint64_t), cudaMemcpyDeviceToHost, p->s_out));
+        if (blob && end <= blob_cap) {
+            if (end > prev) COVA_CUDA(cudaMemcpyAsync(blob + prev, sl.ccl.d_blob + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, p->s_out));
+        } else {
+            too_small = true;
+        }
+        prev = end;
+    }
+    COVA_CUDA(cudaStreamSynchronize(p->s_out));
+    *blob_len = (size_t)prev;
+    if (too_small) return set_err(COVA_E_TOOSMALL, "box blob needs a larger buffer");
+    return COVA_OK;
+}
+
 extern "C" int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, uint8_t *blob,
                                           size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens, uint32_t *n_windows) {
-    int rc = cova_pipeline_load_frames(p, frames, n_streams, fps, 0);
-    if (!rc) rc = cova_pipeline_run(p);
-    if (!rc) rc = cova_pipeline_fetch_boxes(p, blob, blob_cap, blob_len, offsets, lens);
-    if (!rc && n_windows) *n_windows = p->cur_windows;
+    if (!p || !frames || !blob_len) return set_err(COVA_E_INVAL, "null argument");
+    if (p->slot[0].busy || p->slot[1].busy) return set_err(COVA_E_INVAL, "batches submitted asynchronously are still in flight");
+    p->next_submit = p->next_collect = 0;
+    prof_begin(p);
+    int rc = cova_pipeline_submit_host(p, frames, n_streams, fps);
+    if (!rc) rc = cova_pipeline_collect_host(p, blob, blob_cap, blob_len, offsets, lens, n_windows);
+    else p->slot[0].busy = false;
+    if (!rc) rc = cova_pipeline_sync(p);
     return rc;
 }
 
@@ -824,12 +1097,29 @@ extern "C" int cova_pipeline_read_activation(cova_pipeline *p, int layer, float 
     const Geom &g = enc_side ? p->gx[layer] : p->gd[layer - 4];
     const uint4 *src = enc_side ? p->x[layer] : p->d[layer - 4];
     const int C = layer == 0 ? 3 : (enc_side ? kEncCout[layer - 1] : kDecCin[layer - 4]);
-    const int N = (int)p->cur_windows, Tn = g.Tn;
+    const int N = (int)p->ck_windows, Tn = g.Tn;   // activations of the chunk processed last
     shape[0] = N; shape[1] = C; shape[2] = Tn; shape[3] = g.H; shape[4] = g.W;
     size_t n = (size_t)N * C * Tn * g.H * g.W;
     if (cap_floats < n) return set_err(COVA_E_TOOSMALL, "buffer too small");
     int rc = cova_pipeline_sync(p);
     if (rc) return rc;
+    if (layer == 0 && !p->x[0]) {
+        // BlobNet input as the tcgen05 path sees it: per-frame x-pair-packed rows + the window table
+        const Geom &gf = p->gx0f;
+        std::vector<Row8> host((size_t)geom_rows(gf));
+        COVA_CUDA(cudaMemcpy(host.data(), p->x0f, host.size() * sizeof(Row8), cudaMemcpyDeviceToHost));
+        for (int nn = 0; nn < N; nn++)
+            for (int c = 0; c < 3; c++)
+                for (int t = 0; t < kT; t++)
+                    for (int y = 0; y < gf.H; y++)
+                        for (int x = 0; x < gf.W; x++) {
+                            const int f = p->h_newest[nn] - t;
+                            const Row8 &r = host[(size_t)geom_row(gf, 0, (y & 1) << 1, geom_pos(gf, f, y >> 1, x >> 1, 0))];
+                            out[((((size_t)nn * 3 + c) * kT + t) * gf.H + y) * gf.W + x] = __half2float(r.v[(x & 1) * 4 + c]);
+                        }
+        shape[2] = kT;
+        return COVA_OK;
+    }
     std::vector<Row8> host((size_t)geom_rows(g));
     COVA_CUDA(cudaMemcpy(host.data(), src, host.size() * sizeof(Row8), cudaMemcpyDeviceToHost));
     for (int nn = 0; nn < N; nn++)

@@ -70,4 +70,104 @@ __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__res
     }
 }
 
+// (c) per-FRAME BlobNet input for the tcgen05 path: one 16-byte row per horizontal pixel pair,
+//     [c0 c1 c2 0 | c0' c1' c2' 0] (fp16, clipped to 6), in the two row-parity planes (ph = 0 and 2) of a
+//     Tn = 1 phase-plane geometry whose "windows" are the frames of the pool.  The first convolution runs once
+//     per frame on this; the window structure (newest-first stacking of `timestep` frames) is applied afterwards
+//     by pointwise_tn_kernel through the `newest` table.
+__global__ void __launch_bounds__(256) tensorise_frames_kernel(const uint32_t *__restrict__ frames, uint4 *__restrict__ x0f,
+                                                               Geom g, int n_frames) {
+    const int Wh = g.Wh;
+    const long long total = (long long)n_frames * g.H * Wh;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int x2 = (int)(i % Wh);
+        long long r = i / Wh;
+        int y = (int)(r % g.H);
+        int f = (int)(r / g.H);
+        const uint32_t *src = frames + ((long long)f * g.H + y) * g.W + 2 * x2;
+        uint32_t q0 = __ldg(src);
+        uint32_t q1 = (2 * x2 + 1 < g.W) ? __ldg(src + 1) : 0u;
+        __half2 a01 = __floats2half2_rn((float)min(q0 & 0xffu, 6u), (float)min((q0 >> 8) & 0xffu, 6u));
+        __half2 a2z = __floats2half2_rn((float)min((q0 >> 16) & 0xffu, 6u), 0.f);
+        __half2 b01 = __floats2half2_rn((float)min(q1 & 0xffu, 6u), (float)min((q1 >> 8) & 0xffu, 6u));
+        __half2 b2z = __floats2half2_rn((float)min((q1 >> 16) & 0xffu, 6u), 0.f);
+        uint4 row;
+        row.x = *reinterpret_cast<uint32_t *>(&a01); row.y = *reinterpret_cast<uint32_t *>(&a2z);
+        row.z = *reinterpret_cast<uint32_t *>(&b01); row.w = *reinterpret_cast<uint32_t *>(&b2z);
+        x0f[geom_row(g, 0, (y & 1) << 1, geom_pos(g, f, y >> 1, x2, 0))] = row;
+    }
+}
+
+// PointWiseTN of the first encoder block (reference utils/model/pointwise.py:10-26) as a gather over frames:
+// window n, time t reads the pooled per-frame activation of frame newest[n]-t.  Thread <-> (channel block,
+// phase plane, window, position): 4 x 128-bit loads, 8 channels x two 4x4 products, 4 consecutive 16-byte rows
+// out (t interleaved innermost) + the t = 0 row into the decoder's concat buffer.
+struct TnArgs {
+    const uint4 *p1; Geom gp1;       // per-frame pooled activations (Tn = 1, "windows" = frames)
+    uint4 *x1; Geom gx1;             // next encoder input (Tn = 4)
+    uint4 *skip; Geom gskip;         // decoder concat buffer (Tn = 1)
+    int skip_cb;
+    const int *newest;
+    float w1[16], w2[16];
+    int n_windows, CB;
+};
+__global__ void __launch_bounds__(256) pointwise_tn_kernel(const __grid_constant__ TnArgs A) {
+    const int S = A.gx1.S;
+    const long long total = (long long)A.CB * 4 * A.n_windows * S;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int s = (int)(i % S);
+        long long r = i / S;
+        int n = (int)(r % A.n_windows);
+        r /= A.n_windows;
+        int ph = (int)(r & 3), cb = (int)(r >> 2);
+        int y2 = s / A.gx1.P, x2 = s - y2 * A.gx1.P;
+        if (2 * y2 + (ph >> 1) >= A.gx1.H || 2 * x2 + (ph & 1) >= A.gx1.W) continue;   // shared zero row / column
+        const int f0 = A.newest[n];
+        float x[4][8];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            uint4 v = __ldg(A.p1 + geom_row(A.gp1, cb, ph, A.gp1.guard + (long long)(f0 - t) * A.gp1.S + s));
+            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { float2 f = __half22float2(h[k]); x[t][2 * k] = f.x; x[t][2 * k + 1] = f.y; }
+        }
+        uint4 out[4];
+        uint32_t *o32 = reinterpret_cast<uint32_t *>(out);
+        float y[4][8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float h1[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                float h = 0.f;
+#pragma unroll
+                for (int t = 0; t < 4; t++) h = fmaf(x[t][j], A.w1[t * 4 + m], h);
+                h1[m] = fmaxf(h, 0.f);
+            }
+#pragma unroll
+            for (int to = 0; to < 4; to++) {
+                float h = 0.f;
+#pragma unroll
+                for (int m = 0; m < 4; m++) h = fmaf(h1[m], A.w2[m * 4 + to], h);
+                y[to][j] = fmaxf(x[to][j] + fmaxf(h, 0.f), 0.f);
+            }
+        }
+#pragma unroll
+        for (int to = 0; to < 4; to++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                __half2 hh = __floats2half2_rn(y[to][2 * k], y[to][2 * k + 1]);
+                o32[to * 4 + k] = *reinterpret_cast<uint32_t *>(&hh);
+            }
+        uint4 *dst = A.x1 + geom_row(A.gx1, cb, ph, A.gx1.guard + ((long long)n * S + s) * 4);
+#pragma unroll
+        for (int to = 0; to < 4; to++) dst[to] = out[to];
+        A.skip[geom_row(A.gskip, A.skip_cb + cb, ph, A.gskip.guard + (long long)n * S + s)] = out[0];
+    }
+}
+
 }  // namespace cova

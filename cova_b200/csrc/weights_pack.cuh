@@ -76,16 +76,6 @@ inline void put_b(std::vector<__half> &dst, size_t block, int N, int n, int k, f
     dst[block * (size_t)N * 16 + ((size_t)(k >> 3) * N + n) * 8 + (k & 7)] = __float2half_rn(v);
 }
 
-// enc1 (3 input channels padded to one 8-channel row): 5 MMA steps per output phase, each K=16 made of
-// two taps whose operand rows sit a constant distance apart (that distance is the descriptor's LBO).
-// Both the packer and the kernel (blobnet_tc.cuh) use this table.
-struct Enc1Step { int dy0, dx0, dy1, dx1; };   // tap of K half 0 / K half 1; dy1 == 9 -> half 1 unused
-__host__ __device__ inline Enc1Step enc1_step(int a, int j) {
-    if (j < 3) return Enc1Step{j - 1, -1, j - 1, +1};
-    if (j == 3) return a == 0 ? Enc1Step{0, 0, -1, 0} : Enc1Step{-1, 0, 0, 0};
-    return Enc1Step{1, 0, 9, 9};
-}
-
 struct PackedLayer {
     std::vector<__half> b;     // B blocks
     std::vector<float> epi;    // epilogue constants
@@ -100,16 +90,27 @@ inline void pack_encoder(const HostWeights &hw, int i, PackedLayer &pl) {
     auto W = [&](int co, int ci, int dy, int dx) { return e.conv_w[((size_t)(co * ci_n + ci) * 3 + (dy + 1)) * 3 + (dx + 1)]; };
     pl.n_cols = co_n;
     if (i == 0) {
-        pl.blocks = 4 * 5;
-        pl.b.assign((size_t)pl.blocks * co_n * 16, __float2half_rn(0.f));
-        for (int ph = 0; ph < 4; ph++)
-            for (int j = 0; j < 5; j++) {
-                Enc1Step s = enc1_step(ph >> 1, j);
-                for (int co = 0; co < co_n; co++)
-                    for (int ci = 0; ci < ci_n; ci++) {
-                        put_b(pl.b, ph * 5 + j, co_n, co, ci, W(co, ci, s.dy0, s.dx0) / 6.0f);
-                        if (s.dy1 != 9) put_b(pl.b, ph * 5 + j, co_n, co, 8 + ci, W(co, ci, s.dy1, s.dx1) / 6.0f);
+        // frame-level first conv on x-pair-packed rows (blobnet_tc.cuh, issue_tile<ENCF>): 6 blocks of N = 64
+        // rows (4 phases x 16 channels) x K = 16 (two operand tiles of 8: [c0 c1 c2 0 | c0' c1' c2' 0]).
+        pl.blocks = 6;
+        pl.n_cols = 4 * co_n;
+        pl.b.assign((size_t)pl.blocks * pl.n_cols * 16, __float2half_rn(0.f));
+        for (int st = 0; st < 6; st++)
+            for (int half = 0; half < 2; half++) {
+                int u, sx;
+                if (st < 4) { u = st - 1; sx = half - 1; }
+                else { u = (st == 4 ? 0 : -1) + 2 * half; sx = 1; }
+                for (int ph = 0; ph < 4; ph++) {
+                    const int a = ph >> 1, b = ph & 1, dy = u - a;
+                    if (dy < -1 || dy > 1) continue;
+                    for (int bp = 0; bp < 2; bp++) {                 // b' = pixel of the pair
+                        const int dx = 2 * sx + bp - b;
+                        if (dx < -1 || dx > 1) continue;
+                        for (int co = 0; co < co_n; co++)
+                            for (int ci = 0; ci < ci_n; ci++)
+                                put_b(pl.b, st, pl.n_cols, ph * co_n + co, half * 8 + bp * 4 + ci, W(co, ci, dy, dx) / 6.0f);
                     }
+                }
             }
     } else {
         const int kp_n = ci_n / 16;

@@ -33,6 +33,30 @@ def _ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+class PinnedBuffer:
+    """Page-locked host memory (cova_host_alloc) viewed as a numpy array; lets process() overlap copies."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self.shape, self.dtype = tuple(int(v) for v in np.atleast_1d(shape)), np.dtype(dtype)
+        self.nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        self._p = ctypes.c_void_p()
+        check(_lib.load().cova_host_alloc(ctypes.byref(self._p), self.nbytes))
+        buf = (ctypes.c_uint8 * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            _lib.load().cova_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MetaPreprocess:
     """`metapreprocess` element: one instance == one stream == one sliding window."""
 
@@ -156,9 +180,10 @@ class BlobPipeline:
 
     def __init__(self, w_mb: int, h_mb: int, weights_blob: bytes, max_streams: int, max_frames_per_stream: int,
                  timestep: int = 4, gamma: int = 1, cc_threshold: int = 1, device: int = 0,
-                 impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False):
+                 impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False, n_chunks: int = 0):
         self._h = ctypes.c_void_p()
         flags = impl | (_lib.FLAG_KEEP_LOGITS if keep_logits else 0) | (_lib.FLAG_KEEP_STACKED if keep_stacked else 0)
+        flags |= (n_chunks & 0xff) << 16
         self._wbuf = ctypes.create_string_buffer(weights_blob, len(weights_blob))
         check(_lib.load().cova_pipeline_new(ctypes.byref(self._h), device, w_mb, h_mb, timestep, gamma, max_streams,
                                             max_frames_per_stream, ctypes.cast(self._wbuf, ctypes.c_void_p),
@@ -228,15 +253,46 @@ class BlobPipeline:
         The arrays are reused by the next call.  `blob_cap` bounds the host arena (default: worst case)."""
         n = self.n_windows
         cap = blob_cap or n * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
-        if self._blob is None or self._blob.size < cap:
-            self._blob = np.empty(max(cap, 8), dtype=np.uint8)
-            self._offs = np.zeros(max(self.max_streams * self.max_fps, 1), dtype=np.uint64)
-            self._lens = np.zeros(max(self.max_streams * self.max_fps, 1), dtype=np.uint64)
+        self._ensure_out(cap)
         ln = ctypes.c_size_t()
         check(_lib.load().cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln),
                                                     _ptr(self._offs), _ptr(self._lens)))
         self.last_blob_len = ln.value
         return self._blob, self._offs[:n], self._lens[:n]
+
+    def _ensure_out(self, cap: int):
+        if self._blob is None or self._blob.size < cap:
+            nw = max(self.max_streams * self.max_fps, 1)
+            self._pin = [[PinnedBuffer(max(cap, 8)), PinnedBuffer(nw, np.uint64), PinnedBuffer(nw, np.uint64)] for _ in range(2)]
+            self._blob, self._offs, self._lens = (b.array for b in self._pin[0])
+
+    def _worst_case_cap(self, n_windows: int) -> int:
+        return n_windows * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
+
+    # ---- asynchronous streaming form: at most two batches in flight
+    def submit(self, frames: np.ndarray, blob_cap: int | None = None):
+        """Enqueue one batch (copies + kernels) and return immediately.  `frames` should live in page-locked
+        memory (PinnedBuffer) and must stay untouched until the matching collect()."""
+        a = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
+        self._ensure_out(blob_cap or self._worst_case_cap(self.windows_for(a.shape[0], a.shape[1])))
+        check(_lib.load().cova_pipeline_submit_host(self._h, _ptr(a), a.shape[0], a.shape[1]))
+        self._inflight = getattr(self, "_inflight", []) + [a]
+
+    def collect(self, raw: bool = False):
+        """Wait for the oldest submitted batch; same return value as process()."""
+        k = getattr(self, "_collect_idx", 0)
+        self._collect_idx = k ^ 1
+        blob, offs, lens = (b.array for b in self._pin[k])
+        ln, nw = ctypes.c_size_t(), ctypes.c_uint32()
+        check(_lib.load().cova_pipeline_collect_host(self._h, _ptr(blob), blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens),
+                                                     ctypes.byref(nw)))
+        self._inflight.pop(0)
+        self.n_windows, self.last_blob_len = nw.value, ln.value
+        n = nw.value
+        if raw:
+            return blob, offs[:n], lens[:n]
+        return [blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs[:n], lens[:n])]
 
     def fetch_boxes(self) -> list[bytes]:
         blob, offs, lens = self.fetch_boxes_raw()
@@ -245,9 +301,19 @@ class BlobPipeline:
     def process(self, frames: np.ndarray, raw: bool = False, blob_cap: int | None = None):
         """Host frames -> per-window bincode(Vec<Bbox>) blobs (stream-major, time-minor): a list of bytes,
         or with raw=True the (blob, offsets, lens) arrays without per-window Python objects."""
-        self.load_frames(frames)
-        self.run()
-        return self.fetch_boxes_raw(blob_cap) if raw else self.fetch_boxes()
+        a = np.ascontiguousarray(frames, dtype=np.uint8)
+        n_streams, fps = a.shape[0], a.shape[1]
+        assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
+        n = self.windows_for(n_streams, fps)
+        self._ensure_out(blob_cap or self._worst_case_cap(n))
+        self._collect_idx = 0
+        ln, nw = ctypes.c_size_t(), ctypes.c_uint32()
+        check(_lib.load().cova_pipeline_process_host(self._h, _ptr(a), n_streams, fps, _ptr(self._blob), self._blob.size,
+                                                     ctypes.byref(ln), _ptr(self._offs), _ptr(self._lens), ctypes.byref(nw)))
+        self.n_windows, self.last_blob_len = nw.value, ln.value
+        if raw:
+            return self._blob, self._offs[:n], self._lens[:n]
+        return [self._blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(self._offs[:n], self._lens[:n])]
 
     # ---- inspection (parity tests)
     def read_stacked(self) -> np.ndarray:

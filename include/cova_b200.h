@@ -36,6 +36,9 @@ const char *cova_version(void);
 const char *cova_strerror(int code);
 const char *cova_last_error(void);
 int cova_device_count(int *n);
+/* page-locked host memory: frame and box buffers in it let process_host overlap copies with kernels */
+int cova_host_alloc(void **out, size_t bytes);
+void cova_host_free(void *ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * metapreprocess element   (cova-rs/gst-plugins/src/metapreprocess/imp.rs)
@@ -101,6 +104,7 @@ typedef struct cova_pipeline cova_pipeline;
 #define COVA_IMPL_SIMT 1u    /* validation kernels (CUDA cores, fp32 weights) used by the tests */
 #define COVA_FLAG_KEEP_LOGITS 0x100u  /* also store fp32 logits (parity tests) */
 #define COVA_FLAG_KEEP_STACKED 0x200u /* also materialise the stacked RGBA windows (parity tests) */
+#define COVA_FLAG_CHUNKS(n) (((uint32_t)(n) & 0xffu) << 16) /* process a batch in n chunks of whole chains (0 = auto) */
 
 int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb, uint32_t h_mb, uint32_t timestep,
                       uint32_t gamma, uint32_t max_streams, uint32_t max_frames_per_stream, const void *weights,
@@ -130,6 +134,14 @@ int cova_pipeline_fetch_boxes(cova_pipeline *p, uint8_t *blob, size_t blob_cap, 
 int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams,
                                uint32_t frames_per_stream, uint8_t *blob, size_t blob_cap, size_t *blob_len,
                                uint64_t *offsets, uint64_t *lens, uint32_t *n_windows);
+
+/* Asynchronous form of process_host for steady-state streaming: at most two batches in flight.  submit returns
+ * once the copies and kernels are enqueued (frames must stay valid, ideally page-locked, until the matching
+ * collect); collect blocks for the oldest batch and copies its boxes out.  submit(k+1) before collect(k) hides
+ * the host<->device copies of one batch behind the kernels of the other. */
+int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t frames_per_stream);
+int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                               uint64_t *lens, uint32_t *n_windows);
 
 /* feed a mask batch straight to the CCL stage (u8 [n][h_mb][w_mb]; is_device as above) */
 int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, uint32_t n, int is_device);

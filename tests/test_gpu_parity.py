@@ -191,7 +191,7 @@ def test_pipeline_is_deterministic_and_reusable():
     b = synth.synth_streams(2, 7, 45, 80, config_idx=5)
     ra1, rb, ra2 = p.process(a), p.process(b), p.process(a)
     assert ra1 == ra2 and len(rb) == 2 * 4
-    assert p.launch_count() == 3 * 10
+    assert p.launch_count() == 3 * 11        # tensorise, conv1, TN gather, 7 layer kernels, CCL
 
 
 def test_byte3_and_values_above_six_do_not_matter():
@@ -225,3 +225,41 @@ def test_full_size_batch_properties():
     assert (mask[: 8 * 64] == mask[8 * 64:]).all()
     assert 0.01 < mask.mean() < 0.5
     assert p.process(frames) == blobs
+
+
+def test_chunked_overlapped_processing_matches_single_chunk():
+    """process() splits a batch into chunks of whole chains and overlaps copies with kernels; the per-window
+    results must not depend on the chunking (last chunk smaller than the others included)."""
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.synth_streams(7, 9, 45, 80, config_idx=8)
+    one = BlobPipeline(80, 45, weights.to_blob(wts), 7, 9, n_chunks=1)
+    many = BlobPipeline(80, 45, weights.to_blob(wts), 7, 9, n_chunks=3)
+    a, b = one.process(frames), many.process(frames)
+    assert a == b and len(a) == 7 * 6
+    assert (one.read_mask() == many.read_mask()).all()
+    many.load_frames(frames)                      # device-resident path runs the same chunks sequentially
+    many.run()
+    assert many.fetch_boxes() == a
+    with pytest.raises(_lib.CovaError):           # stage-wise calls need a single chunk
+        many.tensorise()
+    assert many.process(frames[:2]) == a[: 2 * 6]
+
+
+def test_async_submit_collect_two_in_flight():
+    wts = weights.random_weights(0, head_bias=-1.0)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 4, 8, n_chunks=2)
+    batches = [synth.synth_streams(4, 8, 45, 80, config_idx=10 + i) for i in range(5)]
+    want = [p.process(b) for b in batches]
+    got = []
+    p.submit(batches[0])
+    for k in range(len(batches)):
+        if k + 1 < len(batches):
+            p.submit(batches[k + 1])
+        got.append(p.collect())
+    assert got == want
+    with pytest.raises(_lib.CovaError):
+        p.collect()                               # nothing in flight
+    p.submit(batches[0]); p.submit(batches[1])
+    with pytest.raises(_lib.CovaError):
+        p.submit(batches[2])                      # at most two in flight
+    assert [p.collect(), p.collect()] == want[:2]
