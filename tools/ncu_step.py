@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""Development aid: N whole-path steps on device-resident frames, for `ncu` captures (profiles/)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cova_b200 import synth, weights
+from cova_b200.elements import BlobPipeline
+
+n_streams, fps = int(os.environ.get("STREAMS", 128)), 67
+h, w = int(os.environ.get("H", 45)), int(os.environ.get("W", 80))
+steps = int(os.environ.get("STEPS", 4))
+p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps)
+p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
+for _ in range(steps):
+    p.run()
+    p.sync()
+print("windows", p.n_windows, "launches", p.launch_count())
