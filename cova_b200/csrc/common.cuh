@@ -67,7 +67,7 @@ inline Geom make_geom(int H, int W, int C, int Tn, int N) {
     g.halo = (g.P + 1) * Tn;
     g.guard = ((g.halo + 7) / 8) * 8;
     long long m = (long long)N * g.S * Tn;
-    m = ((m + kGroupAlign - 1) / kGroupAlign) * kGroupAlign;
+    m = ((m + kGroupAlign - 1) / kGroupAlign) * kGroupAlign + kGroupAlign;   // a whole tile group may over-read
     g.Lp = g.guard + m + g.guard;
     g.N = N;
     return g;
@@ -91,6 +91,33 @@ constexpr int kEncCout[4] = {16, 32, 64, 128};
 constexpr int kDecCin[4] = {128, 128, 64, 32};
 constexpr int kDecCout[4] = {64, 32, 16, 16};
 constexpr float kBnEps = 1e-3f;  // Keras BatchNormalization default (reference encoder.py:45-48)
+
+// packed fp32 pairs (SASS FFMA2 / FADD2 / FMUL2: two fp32 operations per issue slot; ptxas folds {x, x} pairs
+// into broadcast operands)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 relu2(float2 a) { return make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 struct alignas(16) Row8 {  // one 16-byte row: 8 fp16 channels
     __half v[8];

@@ -8,6 +8,7 @@
 
 #include "blobnet_simt.cuh"
 #include "blobnet_tc.cuh"
+#include "blobnet_enc.cuh"
 #include "ccl.cuh"
 #include "common.cuh"
 #include "tensorise.cuh"
@@ -357,6 +358,7 @@ struct cova_pipeline {
     HostWeights hw;
     float *d_wraw = nullptr;
     DevLayer enc[4], dec[4];
+    DevLayer encs[4];                    // blocks 2..4, weights-stationary kernel (blobnet_enc.cuh)
     CclBuffers ccl;
     unsigned int *d_watchdog = nullptr;
     unsigned long long *h_pinned = nullptr;   // cursor + overflow, then offsets/lens staging
@@ -500,6 +502,11 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
         PackedLayer pl;
         pack_encoder(p->hw, i, pl);
         if ((rc = upload_layer(p->enc[i], &pl, 1))) return fail(rc);
+        if (i >= 1) {
+            PackedLayer ws;
+            pack_encoder_ws(p->hw, i, i == 1 ? 2 : 1, i <= 2 ? 2 : 1, ws);
+            if ((rc = upload_layer(p->encs[i], &ws, 1))) return fail(rc);
+        }
     }
     for (int i = 0; i < 4; i++) {
         const int nsplit = i == 0 ? 2 : 1;
@@ -522,6 +529,8 @@ extern "C" void cova_pipeline_free(cova_pipeline *p) {
         if (p->d[i]) cudaFree(p->d[i]);
         if (p->enc[i].wpack) cudaFree(p->enc[i].wpack);
         if (p->enc[i].epi) cudaFree(p->enc[i].epi);
+        if (p->encs[i].wpack) cudaFree(p->encs[i].wpack);
+        if (p->encs[i].epi) cudaFree(p->encs[i].epi);
         if (p->dec[i].wpack) cudaFree(p->dec[i].wpack);
         if (p->dec[i].epi) cudaFree(p->dec[i].epi);
     }
@@ -749,6 +758,23 @@ static int launch_first_fit(const tc::LayerParams &lp, int n_sms, cudaStream_t s
     return rc;
 }
 
+template <class C0, class... Cs>
+static int launch_fit_e(const tc::LayerParams &lp, int n_sms, cudaStream_t st, int min_stage) {
+    cudaError_t err = cudaSuccess;
+    if (tcs::try_launch_e<C0>(lp, n_sms, st, err, min_stage)) {
+        if (err != cudaSuccess) return set_err(COVA_E_CUDA, "tcgen05 encoder launch: %s", cudaGetErrorString(err));
+        return COVA_OK;
+    }
+    if constexpr (sizeof...(Cs) > 0) return launch_fit_e<Cs...>(lp, n_sms, st, min_stage);
+    else return COVA_E_UNSUPPORTED;
+}
+template <class... Cs>
+static int launch_first_fit_e(const tc::LayerParams &lp, int n_sms, cudaStream_t st) {
+    int rc = launch_fit_e<Cs...>(lp, n_sms, st, 2);
+    if (rc == COVA_E_UNSUPPORTED) rc = launch_fit_e<Cs...>(lp, n_sms, st, 1);
+    return rc;
+}
+
 static int tc_layer(cova_pipeline *p, int layer) {
     using namespace tc;
     const int N = (int)p->ck_windows;
@@ -786,12 +812,31 @@ static int tc_layer(cova_pipeline *p, int layer) {
             memcpy(ta.w1, p->hw.enc[0].tn_w1, 64);
             memcpy(ta.w2, p->hw.enc[0].tn_w2, 64);
             long long total = (long long)ta.CB * 4 * N * p->gx[1].S;
+            if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the PointWiseTN gather kernel (32-bit index)");
             int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
             pointwise_tn_kernel<<<blocks, 256, 0, p->stream>>>(ta);
             COVA_CUDA(cudaGetLastError());
             p->launches++;
             prof_mark(p, "enc1_pointwise_tn");
             return COVA_OK;
+        }
+        // block 3 (Cout = 64) stays on the positions-as-M kernel: measured 0.335 ms vs 0.376 ms per 8192 windows at 720p
+        // (profiles/r1c_layer_timing.txt); dbg bit 3 forces the weights-stationary variant for experiments
+        if (!(p->dbg & 4) && (i != 2 || (p->dbg & 8))) {
+            // weights-stationary kernel first; the positions-as-M kernel below remains the fallback for grids
+            // whose strips do not fit shared memory
+            LayerParams ws = lp;
+            ws.wpack = p->encs[i].wpack; ws.epi = p->encs[i].epi;
+            using tcs::ECfg;
+            if (i == 1) rc = launch_first_fit_e<ECfg<2, 32, 2, 2, 192, 3>, ECfg<2, 32, 2, 2, 192, 2>, ECfg<2, 32, 2, 2, 192, 1>>(ws, p->n_sms, p->stream);
+            else if (i == 2) rc = launch_first_fit_e<ECfg<4, 64, 1, 2, 128, 2>, ECfg<4, 64, 1, 2, 128, 1>>(ws, p->n_sms, p->stream);
+            else rc = launch_first_fit_e<ECfg<8, 128, 1, 1, 64, 2>, ECfg<8, 128, 1, 1, 64, 1>>(ws, p->n_sms, p->stream);
+            if (rc != COVA_E_UNSUPPORTED) {
+                if (rc) return rc;
+                p->launches++;
+                prof_mark(p, i == 1 ? "tc_enc2" : i == 2 ? "tc_enc3" : "tc_enc4");
+                return COVA_OK;
+            }
         }
         if (i == 1) rc = launch_first_fit<Cfg<MODE_ENC, 2, 32, 4, 2, 32>, Cfg<MODE_ENC, 2, 32, 2, 2, 32>, Cfg<MODE_ENC, 2, 32, 1, 2, 32>>(lp, p->n_sms, p->stream);
         else if (i == 2) rc = launch_first_fit<Cfg<MODE_ENC, 4, 64, 2, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 4, 64>, Cfg<MODE_ENC, 4, 64, 1, 2, 64>>(lp, p->n_sms, p->stream);

@@ -114,59 +114,48 @@ struct TnArgs {
     int n_windows, CB;
 };
 __global__ void __launch_bounds__(256) pointwise_tn_kernel(const __grid_constant__ TnArgs A) {
-    const int S = A.gx1.S;
-    const long long total = (long long)A.CB * 4 * A.n_windows * S;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        int s = (int)(i % S);
-        long long r = i / S;
-        int n = (int)(r % A.n_windows);
-        r /= A.n_windows;
-        int ph = (int)(r & 3), cb = (int)(r >> 2);
-        int y2 = s / A.gx1.P, x2 = s - y2 * A.gx1.P;
-        if (2 * y2 + (ph >> 1) >= A.gx1.H || 2 * x2 + (ph & 1) >= A.gx1.W) continue;   // shared zero row / column
+    const uint32_t S = (uint32_t)A.gx1.S, P = (uint32_t)A.gx1.P, NW = (uint32_t)A.n_windows;
+    const uint32_t per_plane = NW * S, total = (uint32_t)A.CB * 4u * per_plane;      // host guarantees < 2^32
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t pl = i / per_plane, r = i - pl * per_plane;                    // pl = cb*4 + ph
+        const uint32_t n = r / S, s = r - n * S;
+        const uint32_t y2 = s / P, x2 = s - y2 * P;
+        const uint32_t ph = pl & 3u;
+        if (2 * y2 + (ph >> 1) >= (uint32_t)A.gx1.H || 2 * x2 + (ph & 1) >= (uint32_t)A.gx1.W) continue;   // shared zero row / column
         const int f0 = A.newest[n];
-        float x[4][8];
+        const uint4 *src = A.p1 + ((long long)pl * A.gp1.Lp + A.gp1.guard + (long long)f0 * S + s);
+        uint4 in[4];
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            uint4 v = __ldg(A.p1 + geom_row(A.gp1, cb, ph, A.gp1.guard + (long long)(f0 - t) * A.gp1.S + s));
-            const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+        for (int t = 0; t < 4; t++) in[t] = __ldg(src - (long long)t * S);
+        uint32_t o32[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { float2 f = __half22float2(h[k]); x[t][2 * k] = f.x; x[t][2 * k + 1] = f.y; }
-        }
-        uint4 out[4];
-        uint32_t *o32 = reinterpret_cast<uint32_t *>(out);
-        float y[4][8];
+        for (int k = 0; k < 4; k++) {                       // channel pair (2k, 2k+1); packed lanes = the two channels
+            float2 x[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            float h1[4];
+            for (int t = 0; t < 4; t++) x[t] = __half22float2(reinterpret_cast<const __half2 *>(&in[t])[k]);
+            float2 h1[4];
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-                float h = 0.f;
+                float2 h = fmul2(x[0], bc2(A.w1[m]));
 #pragma unroll
-                for (int t = 0; t < 4; t++) h = fmaf(x[t][j], A.w1[t * 4 + m], h);
-                h1[m] = fmaxf(h, 0.f);
+                for (int t = 1; t < 4; t++) h = ffma2(x[t], bc2(A.w1[t * 4 + m]), h);
+                h1[m] = relu2(h);
             }
 #pragma unroll
             for (int to = 0; to < 4; to++) {
-                float h = 0.f;
+                float2 h = x[to];                            // relu(x + relu(h2)) = max(x + h2, x, 0)
 #pragma unroll
-                for (int m = 0; m < 4; m++) h = fmaf(h1[m], A.w2[m * 4 + to], h);
-                y[to][j] = fmaxf(x[to][j] + fmaxf(h, 0.f), 0.f);
+                for (int m = 0; m < 4; m++) h = ffma2(h1[m], bc2(A.w2[m * 4 + to]), h);
+                const __half2 hh = __floats2half2_rn(fmax3(h.x, x[to].x, 0.f), fmax3(h.y, x[to].y, 0.f));
+                o32[to][k] = *reinterpret_cast<const uint32_t *>(&hh);
             }
         }
+        uint4 *dst = A.x1 + ((long long)pl * A.gx1.Lp + A.gx1.guard + ((long long)n * S + s) * 4);
 #pragma unroll
-        for (int to = 0; to < 4; to++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                __half2 hh = __floats2half2_rn(y[to][2 * k], y[to][2 * k + 1]);
-                o32[to * 4 + k] = *reinterpret_cast<uint32_t *>(&hh);
-            }
-        uint4 *dst = A.x1 + geom_row(A.gx1, cb, ph, A.gx1.guard + ((long long)n * S + s) * 4);
-#pragma unroll
-        for (int to = 0; to < 4; to++) dst[to] = out[to];
-        A.skip[geom_row(A.gskip, A.skip_cb + cb, ph, A.gskip.guard + (long long)n * S + s)] = out[0];
+        for (int to = 0; to < 4; to++) dst[to] = make_uint4(o32[to][0], o32[to][1], o32[to][2], o32[to][3]);
+        A.skip[((long long)(A.skip_cb * 4) + pl) * A.gskip.Lp + A.gskip.guard + (long long)n * S + s] =
+            make_uint4(o32[0][0], o32[0][1], o32[0][2], o32[0][3]);
     }
 }
 

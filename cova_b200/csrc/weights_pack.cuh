@@ -131,6 +131,46 @@ inline void pack_encoder(const HostWeights &hw, int i, PackedLayer &pl) {
     }
 }
 
+
+// Encoder layer i (>= 1) for the weights-stationary kernel (blobnet_enc.cuh): A blocks [iu][iv][kpair], each
+// 128 rows x 16 K (fp16, 32 bytes per row); row m = 32*q + cbl*(8*PL) + lph*8 + j holds output channel
+// (q*CBQ + cbl)*8 + j of lane phase lph = (la, lb).  LA / LB = 2 puts the row / column pooling phase into M
+// ("union of taps": offset u = iu - 1 in [-1, 2] serves tap dy = u - la when that is in [-1, 1]); otherwise the
+// phase is a separate pass and iu indexes the tap directly.  Channels with a negative BatchNorm scale are
+// negated (sgn = -1): max-pooling -conv yields -min(conv), which is what MaxPool(BN(ReLU(.))) needs there.
+// epi = sgn | bias | scale | shift.
+inline void pack_encoder_ws(const HostWeights &hw, int i, int LA, int LB, PackedLayer &pl) {
+    const int ci_n = kEncCin[i], co_n = kEncCout[i], kp_n = ci_n / 16;
+    const auto &e = hw.enc[i];
+    auto W = [&](int co, int ci, int dy, int dx) { return e.conv_w[((size_t)(co * ci_n + ci) * 3 + (dy + 1)) * 3 + (dx + 1)]; };
+    const int PL = LA * LB, NU = LA == 2 ? 4 : 3, NV = LB == 2 ? 4 : 3, CBQ = co_n / 32;
+    pl.blocks = NU * NV * kp_n;
+    pl.n_cols = 128;
+    pl.b.assign((size_t)pl.blocks * 128 * 16, __float2half_rn(0.f));
+    pl.epi.resize(4 * co_n);
+    for (int co = 0; co < co_n; co++) {
+        float s = e.gamma[co] / sqrtf(e.var[co] + kBnEps);
+        pl.epi[co] = s >= 0.f ? 1.f : -1.f;
+        pl.epi[co_n + co] = e.conv_b[co];
+        pl.epi[2 * co_n + co] = s;
+        pl.epi[3 * co_n + co] = e.beta[co] - e.mean[co] * s;
+    }
+    for (int iu = 0; iu < NU; iu++)
+        for (int iv = 0; iv < NV; iv++)
+            for (int kp = 0; kp < kp_n; kp++) {
+                const size_t blk = (size_t)(iu * NV + iv) * kp_n + kp;
+                for (int m = 0; m < 128; m++) {
+                    const int q = m >> 5, l = m & 31, j = l & 7, lph = (l >> 3) & (PL - 1), cbl = l / (8 * PL);
+                    const int co = (q * CBQ + cbl) * 8 + j;
+                    const int lb = LB == 2 ? (lph & 1) : 0, la = LA == 2 ? (LB == 2 ? lph >> 1 : lph & 1) : 0;
+                    const int dy = LA == 2 ? (iu - 1) - la : iu - 1, dx = LB == 2 ? (iv - 1) - lb : iv - 1;
+                    if (dy < -1 || dy > 1 || dx < -1 || dx > 1) continue;
+                    for (int k = 0; k < 16; k++)
+                        pl.b[(blk * 128 + m) * 16 + k] = __float2half_rn(pl.epi[co] * W(co, kp * 16 + k, dy, dx));
+                }
+            }
+}
+
 // Decoder layer i (< 3), N-half `half` of `nsplit`: N = (4/nsplit) parities x Cout; blocks [tap][kpair];
 // epi = scale|offset (per Cout).  Layer 3 (+ head): N = 16 (4 parities used); epi[0] = constant term.
 inline void pack_decoder(const HostWeights &hw, int i, int nsplit, int half, PackedLayer &pl) {

@@ -9,11 +9,11 @@ from cova_b200.elements import BlobPipeline
 
 n_streams, fps = int(os.environ.get("STREAMS", 128)), 67
 h, w = int(os.environ.get("H", 45)), int(os.environ.get("W", 80))
-p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps)
+p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=1)
 p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
 p.set_profiling(True)
 res = {}
-for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither", 3)):
+for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither", 3), ("old_enc", 4)):
     p.set_debug(flags)
     acc = {}
     for _ in range(4):
