@@ -189,9 +189,10 @@ def main():
     # page-locked host frames from the library's own allocator (cova_host_alloc): the library links the CUDA
     # runtime statically, and memory pinned by torch's runtime instance is not seen as pinned by it
     from cova_b200.elements import PinnedBuffer
-    pinned, pinned2 = PinnedBuffer(frames_np.shape), PinnedBuffer(frames_np.shape)
+    pinned, pinned2, pinned3 = (PinnedBuffer(frames_np.shape) for _ in range(3))
     pinned.array[...] = frames_np
     pinned2.array[...] = np.roll(frames_np, 1, axis=0)
+    pinned3.array[...] = np.roll(frames_np, 2, axis=0)
     pipe = BlobPipeline(W_MB, H_MB, weights.to_blob(w), n_streams, fps, cc_threshold=1, device=local_rank,
                         impl=_lib.IMPL_TCGEN05, n_chunks=args.chunks)
     # a real (non-default) stream, shared by torch's events and the library's kernels
@@ -244,20 +245,22 @@ def main():
     kms = {k: float(np.mean(v)) for k, v in acc.items()}
 
     # ---- end to end: pinned host frames -> boxes on the host, through the public streaming call.  Every step copies
-    # its own frames host->device and its boxes device->host inside the timed region; two batches are in flight
-    # (submit k+1, then collect k), so the copies of one batch overlap the kernels of the other.
-    host_frames = [pinned.array, pinned2.array]
+    # its own frames host->device and its boxes device->host inside the timed region; up to three batches are in flight
+    # (submit k+2, then collect k), so the copies of one batch overlap the kernels of another.
+    host_frames = [pinned.array, pinned2.array, pinned3.array]
     pipe.process(host_frames[0], raw=True)
-    pipe.submit(host_frames[0]); pipe.submit(host_frames[1])      # warm both batch slots
-    pipe.collect(raw=True); pipe.collect(raw=True)
+    for hf in host_frames:                                          # warm all three batch slots
+        pipe.submit(hf)
+    for _ in host_frames:
+        pipe.collect(raw=True)
     barrier()
-    e2e_steps = max(4, args.steps // 2)
+    e2e_steps = max(6, args.steps // 2)
     t0 = time.perf_counter()
-    pipe.submit(host_frames[0])
+    pipe.submit(host_frames[0]); pipe.submit(host_frames[1])
     d2h = 0
     for k in range(e2e_steps):
-        if k + 1 < e2e_steps:
-            pipe.submit(host_frames[(k + 1) & 1])
+        if k + 2 < e2e_steps:
+            pipe.submit(host_frames[(k + 2) % 3])
         blob, offs, lens = pipe.collect(raw=True)
         d2h = pipe.last_blob_len + 16 * n_windows + 16
     torch.cuda.synchronize()

@@ -320,6 +320,8 @@ struct DevLayer {
     int n_cols = 0;
 };
 
+constexpr int kSlots = 3;
+
 struct cova_pipeline {
     int device = 0, n_sms = 0;
     uint32_t W = 0, H = 0, T = 0, gamma = 1, max_streams = 0, max_fps = 0, max_windows = 0, flags = 0, impl = 0;
@@ -334,8 +336,9 @@ struct cova_pipeline {
     uint32_t chunk_streams = 0;          // chains per chunk (capacity)
     uint32_t ck_stream0 = 0, ck_n_streams = 0, ck_window0 = 0, ck_windows = 0;   // chunk being processed
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    // Two batch slots (frame pool + box arena + events) so that submit_host(k+1) can copy in while batch k computes
-    // and batch k-1's boxes copy out.  The synchronous entry points use slot 0.
+    // Three batch slots (frame pool + box arena + events): submit_host(k+2) can be queued before collect_host(k), so
+    // the host->device copy engine never waits for a device->host copy whose size the host must first learn.
+    // The synchronous entry points use slot 0.
     struct Slot {
         uint8_t *d_frames = nullptr;
         CclBuffers ccl;
@@ -343,7 +346,7 @@ struct cova_pipeline {
         unsigned long long *h_cursor = nullptr;      // pinned: per-chunk cursor snapshots (2 words each)
         uint32_t n_streams = 0, fps = 0, n_windows = 0;
         bool busy = false;
-    } slot[2];
+    } slot[kSlots];
     int cur_slot = 0, next_submit = 0, next_collect = 0;
     int sizes_h[5], sizes_w[5];          // extents: [0] input, [1..4] encoder outputs
     Geom gx[4];                          // X0..X3 (Tn = 4): inputs of enc1..enc4
@@ -492,9 +495,9 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     p->slot[0].ccl.d_masks = p->d_mask;
     if ((rc = ccl_alloc(p->slot[0].ccl, (int)h_mb, (int)w_mb, std::max(1, NB), false))) return fail(rc);
     p->ccl = p->slot[0].ccl;
-    if (cudaMallocHost(&p->slot[0].h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess ||
-        cudaMallocHost(&p->slot[1].h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess)
-        return fail(set_err(COVA_E_CUDA, "pinned allocation failed"));
+    for (auto &sl : p->slot)
+        if (cudaMallocHost(&sl.h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess)
+            return fail(set_err(COVA_E_CUDA, "pinned allocation failed"));
 
     // weights: raw fp32 for the validation kernels, packed fp16 operand blocks for the tcgen05 path
     if ((rc = dev_upload(&p->d_wraw, p->hw.storage.data(), p->hw.storage.size() * sizeof(float)))) return fail(rc);
@@ -1012,8 +1015,8 @@ static void use_slot(cova_pipeline *p, int k) {
     p->d_frames = p->slot[k].d_frames;
     p->ccl = p->slot[k].ccl;
 }
-static int ensure_slot1(cova_pipeline *p) {
-    auto &sl = p->slot[1];
+static int ensure_slot(cova_pipeline *p, int k) {
+    auto &sl = p->slot[k];
     if (sl.d_frames) return COVA_OK;
     COVA_CUDA(cudaMalloc(&sl.d_frames, p->frame_bytes * p->max_streams * p->max_fps));
     sl.ccl.d_masks = p->d_mask;
@@ -1021,22 +1024,22 @@ static int ensure_slot1(cova_pipeline *p) {
 }
 
 // Host frames in, boxes out, asynchronously.  Three streams: the H2D copy of chunk c+1, the kernels of chunk c and
-// the D2H copy of earlier boxes overlap; with two batches in flight (submit k+1 before collect k) the copies of
-// one batch hide behind the kernels of the other.  A chunk's boxes occupy one contiguous range of the slot's device
+// the D2H copy of earlier boxes overlap; with up to three batches in flight (submit k+2 before collect k) the copies
+// of one batch hide behind the kernels of another and the H2D engine is never idle.  A chunk's boxes occupy one contiguous range of the slot's device
 // arena (the cursor is only reset at the start of a batch), so each chunk needs exactly one blob copy of exactly
 // the bytes it produced.
 extern "C" int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps) {
     if (!p || !frames) return set_err(COVA_E_INVAL, "null argument");
     COVA_CUDA(cudaSetDevice(p->device));
     const int k = p->next_submit;
-    if (p->slot[k].busy) return set_err(COVA_E_INVAL, "two batches are already in flight: collect one first");
-    int rc = k == 1 ? ensure_slot1(p) : COVA_OK;
+    if (p->slot[k].busy) return set_err(COVA_E_INVAL, "three batches are already in flight: collect one first");
+    int rc = k > 0 ? ensure_slot(p, k) : COVA_OK;
     if (rc) return rc;
     if ((rc = set_batch_shape(p, n_streams, fps))) return rc;
     use_slot(p, k);
     auto &sl = p->slot[k];
     sl.n_streams = n_streams; sl.fps = fps; sl.n_windows = p->cur_windows; sl.busy = true;
-    p->next_submit = k ^ 1;
+    p->next_submit = (k + 1) % kSlots;
     if (!p->cur_windows) return COVA_OK;
     const uint32_t nc = n_chunks_of(p);
     const size_t chain_bytes = p->frame_bytes * fps;
@@ -1062,7 +1065,7 @@ extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_
     auto &sl = p->slot[k];
     if (!sl.busy) return set_err(COVA_E_INVAL, "no batch in flight");
     sl.busy = false;
-    p->next_collect = k ^ 1;
+    p->next_collect = (k + 1) % kSlots;
     if (n_windows) *n_windows = sl.n_windows;
     *blob_len = 0;
     if (!sl.n_windows) return COVA_OK;
@@ -1094,7 +1097,8 @@ extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_
 extern "C" int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, uint8_t *blob,
                                           size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens, uint32_t *n_windows) {
     if (!p || !frames || !blob_len) return set_err(COVA_E_INVAL, "null argument");
-    if (p->slot[0].busy || p->slot[1].busy) return set_err(COVA_E_INVAL, "batches submitted asynchronously are still in flight");
+    for (auto &sl : p->slot)
+        if (sl.busy) return set_err(COVA_E_INVAL, "batches submitted asynchronously are still in flight");
     p->next_submit = p->next_collect = 0;
     prof_begin(p);
     int rc = cova_pipeline_submit_host(p, frames, n_streams, fps);

@@ -135,7 +135,7 @@ int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t
                                uint32_t frames_per_stream, uint8_t *blob, size_t blob_cap, size_t *blob_len,
                                uint64_t *offsets, uint64_t *lens, uint32_t *n_windows);
 
-/* Asynchronous form of process_host for steady-state streaming: at most two batches in flight.  submit returns
+/* Asynchronous form of process_host for steady-state streaming: at most three batches in flight.  submit returns
  * once the copies and kernels are enqueued (frames must stay valid, ideally page-locked, until the matching
  * collect); collect blocks for the oldest batch and copies its boxes out.  submit(k+1) before collect(k) hides
  * the host<->device copies of one batch behind the kernels of the other. */

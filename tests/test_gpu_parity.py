@@ -245,7 +245,7 @@ def test_chunked_overlapped_processing_matches_single_chunk():
     assert many.process(frames[:2]) == a[: 2 * 6]
 
 
-def test_async_submit_collect_two_in_flight():
+def test_async_submit_collect_batches_in_flight():
     wts = weights.random_weights(0, head_bias=-1.0)
     p = BlobPipeline(80, 45, weights.to_blob(wts), 4, 8, n_chunks=2)
     batches = [synth.synth_streams(4, 8, 45, 80, config_idx=10 + i) for i in range(5)]
@@ -259,7 +259,14 @@ def test_async_submit_collect_two_in_flight():
     assert got == want
     with pytest.raises(_lib.CovaError):
         p.collect()                               # nothing in flight
-    p.submit(batches[0]); p.submit(batches[1])
+    p.submit(batches[0]); p.submit(batches[1]); p.submit(batches[2])
     with pytest.raises(_lib.CovaError):
-        p.submit(batches[2])                      # at most two in flight
-    assert [p.collect(), p.collect()] == want[:2]
+        p.submit(batches[3])                      # at most three in flight
+    assert [p.collect(), p.collect(), p.collect()] == want[:3]
+    got = []                                      # two ahead: submit k+2 before collect k
+    p.submit(batches[0]); p.submit(batches[1])
+    for k in range(len(batches)):
+        if k + 2 < len(batches):
+            p.submit(batches[k + 2])
+        got.append(p.collect())
+    assert got == want
