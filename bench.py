@@ -28,22 +28,29 @@ sys.path.insert(0, ROOT)
 H_MB, W_MB, T = 45, 80, 4
 STREAMS_PER_GPU, FRAMES_PER_STREAM = 128, 67
 METRIC, UNIT = "blob_detection_frames_per_sec", "frames/s"
-# BlobNet layer -> kernels that implement it (the first block is a per-frame conv kernel + a PointWiseTN gather)
-LAYER_KERNELS = [("enc1", ["tc_enc1_conv", "enc1_pointwise_tn"]), ("enc2", ["tc_enc2"]), ("enc3", ["tc_enc3"]), ("enc4", ["tc_enc4"]),
-                 ("dec0", ["tc_dec0"]), ("dec1", ["tc_dec1"]), ("dec2", ["tc_dec2"]), ("dec3_head", ["tc_dec3_head"])]
+# kernels of one step in launch order: (name the library reports, bound, BlobNet layer it belongs to)
+KERNELS = [("tensorise_frames", "hbm", None), ("tc_enc1_conv", "tensor", "enc1"), ("enc1_pointwise_tn", "hbm", "enc1"),
+           ("tc_enc2", "tensor", "enc2"), ("tc_enc3", "tensor", "enc3"), ("tc_enc4", "tensor", "enc4"),
+           ("tc_dec0", "tensor", "dec0"), ("tc_dec1", "tensor", "dec1"), ("tc_dec2", "tensor", "dec2"),
+           ("tc_dec3_head", "tensor", "dec3_head"), ("ccl_bbox", "hbm", None)]
+LAYERS = ["enc1", "enc2", "enc3", "enc4", "dec0", "dec1", "dec2", "dec3_head"]
 
 
 def layer_flops(h, w):
-    """Algorithmic 2*MAC per window of every BlobNet layer kernel (PointWiseTN is
-    counted with its encoder layer, the 1x1 head with dec3)."""
+    """Algorithmic 2*MAC per window of every BlobNet layer (PointWiseTN is counted with
+    its encoder layer, the 1x1 head with dec3), plus the PointWiseTN share of the first block."""
     enc_ch = [(3, 16), (16, 32), (32, 64), (64, 128)]
     dec_ch = [(128, 64), (128, 32), (64, 16), (32, 16)]
     out, sizes = [], []
     hh, ww = h, w
-    for ci, co in enc_ch:
+    tn1 = 0
+    for i, (ci, co) in enumerate(enc_ch):
         mac = T * hh * ww * 9 * ci * co
         hh, ww = (hh + 1) // 2, (ww + 1) // 2
-        mac += co * hh * ww * 2 * T * T
+        tn = co * hh * ww * 2 * T * T
+        if i == 0:
+            tn1 = 2 * tn
+        mac += tn
         sizes.append((hh, ww))
         out.append(2 * mac)
     for i, (ci, co) in enumerate(dec_ch):
@@ -52,7 +59,23 @@ def layer_flops(h, w):
         if i == 3:
             mac += h * w * co
         out.append(2 * mac)
-    return out
+    return dict(zip(LAYERS, out)), tn1
+
+
+def kernel_work(h, w, n_boxes):
+    """ALGORITHMIC work per window of every kernel: FLOPs for the tensor-bound ones, bytes for the HBM-bound ones
+    (DESIGN.md section 3)."""
+    fl, tn1 = layer_flops(h, w)
+    h1, w1 = (h + 1) // 2, (w + 1) // 2
+    work = {"tensorise_frames": 20 * h * w,                                   # each frame read once + RGBA stack written
+            "tc_enc1_conv": fl["enc1"] - tn1,
+            # gather: one new pooled frame read (16 ch fp16) + the window's 4 time planes + the t=0 skip copy written
+            "enc1_pointwise_tn": 16 * h1 * w1 * 2 * (1 + T + 1),
+            "ccl_bbox": h * w + 24 * n_boxes + 8}
+    for name, _, layer in KERNELS:
+        if name not in work:
+            work[name] = fl[layer]
+    return work, fl
 
 
 def peaks():
@@ -272,29 +295,36 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        fl = layer_flops(H_MB, W_MB)
+        nbox = float(((lens.astype(np.int64) - 8) // 24).mean())
+        work, fl = kernel_work(H_MB, W_MB, nbox)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("windows_per_launch") == n_windows:
+                traffic = tj["dram_bytes_per_launch"]
         stages = {}
-        layer_ms = {}
-        for (name, kernels), f in zip(LAYER_KERNELS, fl):
-            ms = sum(kms.get(k, 0.0) for k in kernels)
-            layer_ms[name] = ms
-            tf = f * n_windows / (ms * 1e-3) / 1e12
-            stages[name] = {"ms": round(ms, 4), "kernels": {k: round(kms.get(k, 0.0), 4) for k in kernels},
-                            "bound": "tensor", "achieved_tflops": round(tf, 1), "frac": round(tf / pk["tflops"], 4)}
-        if "tensorise_frames" in kms:
-            gb = 20 * H_MB * W_MB * n_windows / (kms["tensorise_frames"] * 1e-3) / 1e9
-            stages["tensorise"] = {"ms": round(kms["tensorise_frames"], 4), "bound": "hbm", "achieved_gbs": round(gb, 1),
-                                   "frac": round(gb / pk["hbm_gbs"], 4)}
-        if "ccl_bbox" in kms:
-            nbox = float(((lens.astype(np.int64) - 8) // 24).mean())
-            gb = (H_MB * W_MB + 24 * nbox + 8) * n_windows / (kms["ccl_bbox"] * 1e-3) / 1e9
-            stages["ccl_bbox"] = {"ms": round(kms["ccl_bbox"], 4), "bound": "hbm", "achieved_gbs": round(gb, 1),
-                                  "frac": round(gb / pk["hbm_gbs"], 5), "boxes_per_frame": round(nbox, 2)}
-        dom = max(layer_ms, key=lambda k: layer_ms[k])
-        roof = {"bound": "tensor", "kernel": "+".join(dict(LAYER_KERNELS)[dom]), "achieved": stages[dom]["achieved_tflops"],
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": stages[dom]["frac"], "traffic": None,
-                "peak_source": pk["source"] + " (sustained bf16, kernel timed inside the step)",
-                "whole_blobnet_frac": round(sum(fl) * n_windows / (sum(layer_ms.values()) * 1e-3) / 1e12 / pk["tflops"], 4)}
+        for name, bound, layer in KERNELS:
+            ms = kms.get(name)
+            if not ms:
+                continue
+            per_s = work[name] * n_windows / (ms * 1e-3)
+            st = {"ms": round(ms, 4), "bound": bound, "layer": layer, "traffic": traffic.get(name)}
+            if bound == "tensor":
+                st.update(achieved=round(per_s / 1e12, 1), unit="TFLOP/s", peak=pk["tflops"], frac=round(per_s / 1e12 / pk["tflops"], 4))
+            else:
+                st.update(achieved=round(per_s / 1e9, 1), unit="GB/s", peak=pk["hbm_gbs"], frac=round(per_s / 1e9 / pk["hbm_gbs"], 4))
+            stages[name] = st
+        stages["ccl_bbox"]["boxes_per_frame"] = round(nbox, 2)
+        blobnet_ms = sum(stages[n]["ms"] for n, _, layer in KERNELS if layer and n in stages)
+        dom = max(stages, key=lambda k: stages[k]["ms"])
+        roof = {"bound": stages[dom]["bound"], "kernel": dom, "achieved": stages[dom]["achieved"], "peak": stages[dom]["peak"],
+                "unit": stages[dom]["unit"], "frac": stages[dom]["frac"], "traffic": stages[dom]["traffic"],
+                "ms_per_launch": stages[dom]["ms"], "share_of_step": round(stages[dom]["ms"] / ms_step, 3),
+                "peak_source": pk["source"] + (" (sustained bf16, kernel timed inside the step)" if stages[dom]["bound"] == "tensor"
+                                               else " (STREAM-style copy)"),
+                "traffic_source": "profiles/traffic.json (ncu --set full of the same workload)" if stages[dom]["traffic"] else None,
+                "whole_blobnet_frac": round(sum(fl.values()) * n_windows / (blobnet_ms * 1e-3) / 1e12 / pk["tflops"], 4)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = time_cpu(w, 2, 1)

@@ -816,6 +816,8 @@ static int tc_layer(cova_pipeline *p, int layer) {
             memcpy(ta.w2, p->hw.enc[0].tn_w2, 64);
             long long total = (long long)ta.CB * 4 * N * p->gx[1].S;
             if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the PointWiseTN gather kernel (32-bit index)");
+            // 16 CTAs per SM queued (4-5 resident): measured faster than a grid of exactly the resident CTAs
+            // (0.43 vs 0.49 ms per 8192 windows) - the hardware CTA scheduler balances the tail
             int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
             pointwise_tn_kernel<<<blocks, 256, 0, p->stream>>>(ta);
             COVA_CUDA(cudaGetLastError());
