@@ -811,14 +811,16 @@ static int tc_layer(cova_pipeline *p, int layer) {
             prof_mark(p, "tc_enc1_conv");
             TnArgs ta;
             ta.p1 = p->p1; ta.gp1 = p->gp1; ta.x1 = p->x[1]; ta.gx1 = p->gx[1]; ta.skip = p->d[3]; ta.gskip = p->gd[3];
-            ta.skip_cb = kDecCout[2] / 8; ta.newest = p->d_newest; ta.n_windows = N; ta.CB = kEncCout[0] / 8;
+            ta.skip_cb = kDecCout[2] / 8; ta.newest = p->d_newest; ta.n_windows = N;
+            ta.wps = windows_per_stream(p->cur_fps, p->T, p->gamma); ta.fps = p->cur_fps; ta.gamma = p->gamma; ta.first = p->T - 1; ta.CB = kEncCout[0] / 8;
             memcpy(ta.w1, p->hw.enc[0].tn_w1, 64);
             memcpy(ta.w2, p->hw.enc[0].tn_w2, 64);
             long long total = (long long)ta.CB * 4 * N * p->gx[1].S;
             if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the PointWiseTN gather kernel (32-bit index)");
-            // 16 CTAs per SM queued (4-5 resident): measured faster than a grid of exactly the resident CTAs
-            // (0.43 vs 0.49 ms per 8192 windows) - the hardware CTA scheduler balances the tail
-            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 16);
+            // 64 CTAs per SM queued (4-5 resident) - measured sweep per 8192 windows at 720p: resident-only grid 0.49 ms,
+            // x16 0.43, x64 0.39, one iteration per thread 0.45
+            static const int tn_factor = getenv("COVA_TN_GRID") ? atoi(getenv("COVA_TN_GRID")) : 64;   // development knob
+            int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * tn_factor);
             pointwise_tn_kernel<<<blocks, 256, 0, p->stream>>>(ta);
             COVA_CUDA(cudaGetLastError());
             p->launches++;
