@@ -30,8 +30,6 @@ namespace tcs {
 
 using tc::LayerParams;
 
-constexpr int kEpiWarps = 16;                   // 4 per TMEM lane quarter (column quarters of a tile)
-constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStage = 4;
 constexpr int kMaxSlot = 4;
 
@@ -63,8 +61,10 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t x, FastDiv f) {
     return (t + ((x - t) >> 1)) >> f.s;
 }
 
-template <int CIN_CB_, int COUT_, int LA_, int LB_, int NP_, int TPS_>
+template <int CIN_CB_, int COUT_, int LA_, int LB_, int NP_, int TPS_, int EW_ = 16>
 struct ECfg {
+    static constexpr int EW = EW_, CS = EW_ / 4;           // epilogue warps: CS per TMEM lane quarter, each owning a column range of a tile
+    static constexpr int THREADS = 64 + 32 * EW_;
     static constexpr int CIN_CB = CIN_CB_, COUT = COUT_, LA = LA_, LB = LB_, NP = NP_, TPS = TPS_;
     static constexpr int PL = LA * LB;                     // pooling phases that live in M (lanes)
     static constexpr int PA = 2 / LA, PB = 2 / LB, PASSES = PA * PB;
@@ -74,7 +74,7 @@ struct ECfg {
     static constexpr int A_COLS = NBLK * 8;
     static constexpr int NSLOT = ((512 - A_COLS) / NP) < kMaxSlot ? ((512 - A_COLS) / NP) : kMaxSlot;
     static constexpr int NUN = NP / 16;                    // 16-column units (4 pixels x 4 frames) per tile
-    static constexpr int UB = NUN / 4, UR = NUN % 4;       // units per epilogue warp: UB (+1 for the first UR column quarters)
+    static constexpr int UB = NUN / CS, UR = NUN % CS;     // units per epilogue warp: UB (+1 for the first UR column ranges)
     static constexpr int MAXU = UB + (UR ? 1 : 0);
     static constexpr int NIT = 4 / PL;                     // (channel block) items per thread and group
     static constexpr int CBQ = COUT / 32;                  // output channel blocks per TMEM lane quarter (= NIT)
@@ -236,7 +236,7 @@ __device__ __forceinline__ void finalize_unit(const LayerParams &p, const float 
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <class C>
-__global__ void __launch_bounds__(kThreads, 1) enc_ws_kernel(const __grid_constant__ LayerParams p, const __grid_constant__ ELayerExtra ex) {
+__global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_constant__ LayerParams p, const __grid_constant__ ELayerExtra ex) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const SmemPlanE sp = plan_smem_e<C>(p.Ls, p.n_stage);
     const uint32_t smem_base = tc::smem_u32(smem);
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_ws_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
 
-    for (int i = threadIdx.x; i < 4 * C::COUT + 32; i += kThreads) {
+    for (int i = threadIdx.x; i < 4 * C::COUT + 32; i += C::THREADS) {
         float v;
         if (i >= 4 * C::COUT) v = (i - 4 * C::COUT < 16) ? p.tn_w1[i - 4 * C::COUT] : p.tn_w2[i - 4 * C::COUT - 16];
         else v = p.epi[i];
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_ws_kernel(const __grid_consta
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStage; s++) { tc::mbar_init(full0 + 8u * s, 1); tc::mbar_init(empty0 + 8u * s, 1); }
-        for (int s = 0; s < kMaxSlot; s++) { tc::mbar_init(tfull0 + 8u * s, 1); tc::mbar_init(tempty0 + 8u * s, kEpiWarps); }
+        for (int s = 0; s < kMaxSlot; s++) { tc::mbar_init(tfull0 + 8u * s, 1); tc::mbar_init(tempty0 + 8u * s, C::EW); }
         tc::fence_barrier_init();
     }
     if (warp == 1) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_ws_kernel(const __grid_consta
     if (warp >= 2) {
         const int q = warp & 3, cq = (warp - 2) >> 2;
         const uint4 *src = p.wpack + (size_t)(q * 32 + lane) * 2;
-        for (int blk = cq; blk < C::NBLK; blk += kEpiWarps / 4) {
+        for (int blk = cq; blk < C::NBLK; blk += C::CS) {
             const uint4 a = __ldg(src + (size_t)blk * 256), b = __ldg(src + (size_t)blk * 256 + 1);
             tmem_st8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 8), a, b);
         }
@@ -467,7 +467,7 @@ inline bool try_launch_e(LayerParams p, int n_sms, cudaStream_t st, cudaError_t 
     ex.divP = make_fastdiv((uint32_t)p.gin.P);
     int ctas = std::min(n_sms, p.n_groups);
     if (ctas < 1) ctas = 1;
-    enc_ws_kernel<C><<<ctas, kThreads, sp.total, st>>>(p, ex);
+    enc_ws_kernel<C><<<ctas, C::THREADS, sp.total, st>>>(p, ex);
     err = cudaGetLastError();
     return true;
 }
