@@ -156,10 +156,13 @@ def test_tensorise_and_blobnet_against_oracle(h, w, n_streams, fps, seed):
             assert box[4] == box[2] * box[3]
 
 
-def test_tcgen05_layers_match_validation_kernels_layer_by_layer():
+@pytest.mark.parametrize("h,w,n_streams,fps", [(45, 80, 2, 8), (68, 120, 1, 6), (135, 240, 1, 5), (33, 47, 1, 5)])
+def test_tcgen05_layers_match_validation_kernels_layer_by_layer(h, w, n_streams, fps):
+    """Every tcgen05 layer kernel (positions-as-M and weights-stationary) in isolation, on identical inputs, against the
+    fp32 validation kernels - at the 720p, 1080p and 4K grids of BASELINE.json and at an odd grid."""
     wts = weights.random_weights(11, head_bias=-1.0)
-    frames = synth.synth_streams(2, 8, 45, 80, config_idx=2)
-    p = BlobPipeline(80, 45, weights.to_blob(wts), 2, 8, impl=_lib.IMPL_SIMT, keep_logits=True)
+    frames = synth.synth_streams(n_streams, fps, h, w, config_idx=2)
+    p = BlobPipeline(w, h, weights.to_blob(wts), n_streams, fps, impl=_lib.IMPL_SIMT, keep_logits=True)
     p.load_frames(frames)
     p.run()
     ref_act = {layer: p.read_activation(layer) for layer in range(8)}
@@ -172,6 +175,29 @@ def test_tcgen05_layers_match_validation_kernels_layer_by_layer():
             p.run_layer(layer, _lib.IMPL_SIMT)
         else:
             assert np.abs(p.read_logits() - ref_logits).max() <= 4e-3 * np.abs(ref_logits).max()
+
+
+def test_negative_batchnorm_scales_and_forced_weights_stationary_block3():
+    """MaxPool(BN(ReLU(x))) with a negative BN scale is BN(ReLU(min x)): the weights-stationary kernel negates those
+    channels' weights (sgn = -1), the positions-as-M kernel switches to a min-pool.  Debug bit 3 routes block 3 through
+    the weights-stationary kernel as well (2 passes, column phases in M)."""
+    wts = weights.random_weights(5, head_bias=-1.0)
+    for i in range(4):
+        g = wts[f"enc{i}.bn_gamma"]
+        g[::3] = -g[::3]
+    frames = synth.synth_streams(2, 7, 45, 80, config_idx=9)
+    _, logit_ref, refs = _oracle(wts, frames)
+    for dbg in (0, 8, 4):
+        p = BlobPipeline(80, 45, weights.to_blob(wts), 2, 7, keep_logits=True)
+        p.set_debug(dbg)
+        p.process(frames)
+        for layer in range(1, 5):
+            a = p.read_activation(layer)
+            err = np.abs(a - refs[layer]).max() / (np.abs(refs[layer]).max() + 1e-12)
+            assert err < ACT_REL_TOL, (dbg, layer, err)
+        logits = p.read_logits()
+        assert np.abs(logits - logit_ref).max() <= LOGIT_REL_TOL * np.abs(logit_ref).max()
+        assert ((logits > 0) != (logit_ref > 0)).mean() <= MAX_FLIP
 
 
 def test_gamma_subsampling_and_chain_restart():
