@@ -63,6 +63,10 @@ def main():
     print(f"{n} frames of {w_mb}x{h_mb}, md5 {md5}, {int(key.sum())} key frames, "
           f"mb_weight histogram {(hist / hist.sum()).round(4).tolist()}, byte3 max {int(frames[..., 3].max())}, "
           f"fixture {os.path.getsize(OUT) / 1e6:.2f} MB")
+    if "--keep" not in sys.argv:          # the snapshot sent to the GPU box should not carry 60 MB of objects
+        import shutil
+        os.remove(raw)
+        shutil.rmtree(BUILD, ignore_errors=True)
 
 
 if __name__ == "__main__":
