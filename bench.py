@@ -29,7 +29,8 @@ H_MB, W_MB, T = 45, 80, 4
 STREAMS_PER_GPU, FRAMES_PER_STREAM = 128, 67
 METRIC, UNIT = "blob_detection_frames_per_sec", "frames/s"
 # kernels of one step in launch order: (name the library reports, bound, BlobNet layer it belongs to)
-KERNELS = [("tensorise_frames", "hbm", None), ("tc_enc1_conv", "tensor", "enc1"), ("enc1_pointwise_tn", "hbm", "enc1"),
+KERNELS = [("tensorise_frames", "hbm", None), ("tc_enc1_fused", "hbm", "enc1"),
+           ("tc_enc1_conv", "tensor", "enc1"), ("enc1_pointwise_tn", "hbm", "enc1"),      # two-kernel fallback of block 1
            ("tc_enc2", "tensor", "enc2"), ("tc_enc3", "tensor", "enc3"), ("tc_enc4", "tensor", "enc4"),
            ("tc_dec0", "tensor", "dec0"), ("tc_dec1", "tensor", "dec1"), ("tc_dec2", "tensor", "dec2"),
            ("tc_dec3_head", "tensor", "dec3_head"), ("ccl_bbox", "hbm", None)]
@@ -68,6 +69,8 @@ def kernel_work(h, w, n_boxes):
     fl, tn1 = layer_flops(h, w)
     h1, w1 = (h + 1) // 2, (w + 1) // 2
     work = {"tensorise_frames": 20 * h * w,                                   # each frame read once + RGBA stack written
+            # fused block 1: one packed input frame read + the window's 4 time planes + the t=0 skip copy written
+            "tc_enc1_fused": 16 * h * ((w + 1) // 2) + 16 * h1 * w1 * 2 * (T + 1),
             "tc_enc1_conv": fl["enc1"] - tn1,
             # gather: one new pooled frame read (16 ch fp16) + the window's 4 time planes + the t=0 skip copy written
             "enc1_pointwise_tn": 16 * h1 * w1 * 2 * (1 + T + 1),

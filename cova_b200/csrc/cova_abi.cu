@@ -9,6 +9,7 @@
 #include "blobnet_simt.cuh"
 #include "blobnet_tc.cuh"
 #include "blobnet_enc.cuh"
+#include "blobnet_enc1.cuh"
 #include "ccl.cuh"
 #include "common.cuh"
 #include "tensorise.cuh"
@@ -803,6 +804,23 @@ static int tc_layer(cova_pipeline *p, int layer) {
         if (i == 0) {
             // first block: conv+ReLU+BN+pool once per FRAME, then PointWiseTN gathers the 4 frames of every window
             const int F = (int)(p->ck_n_streams * p->cur_fps);
+            if (!(p->dbg & 16)) {
+                // fused: frame-level conv + PointWiseTN over a register ring of 4 frames, one kernel (blobnet_enc1.cuh);
+                // dbg bit 4 forces the two-kernel path below (also the fallback for grids the fused kernel cannot take)
+                LayerParams fp = lp;
+                fp.in = p->x0f; fp.gin = p->gx0f; fp.out = p->x[1]; fp.gout = p->gx[1]; fp.N = F;
+                tc1::Enc1Extra ex;
+                memset(&ex, 0, sizeof(ex));
+                ex.n_chains = (int)p->ck_n_streams; ex.fps = (int)p->cur_fps; ex.wps = (int)windows_per_stream(p->cur_fps, p->T, p->gamma);
+                ex.gamma = (int)p->gamma; ex.first = (int)p->T - 1;
+                cudaError_t err = cudaSuccess;
+                if (tc1::try_launch_enc1(fp, ex, p->n_sms, p->stream, err)) {
+                    if (err != cudaSuccess) return set_err(COVA_E_CUDA, "fused enc1 launch: %s", cudaGetErrorString(err));
+                    p->launches++;
+                    prof_mark(p, "tc_enc1_fused");
+                    return COVA_OK;
+                }
+            }
             lp.in = p->x0f; lp.gin = p->gx0f; lp.out = p->p1; lp.gout = p->gp1; lp.out2 = nullptr; lp.N = F;
             rc = launch_first_fit<Cfg<MODE_ENCF, 1, 16, 8, 1, 16>, Cfg<MODE_ENCF, 1, 16, 4, 1, 16>, Cfg<MODE_ENCF, 1, 16, 2, 1, 16>,
                                   Cfg<MODE_ENCF, 1, 16, 1, 1, 16>>(lp, p->n_sms, p->stream);

@@ -200,6 +200,26 @@ def test_negative_batchnorm_scales_and_forced_weights_stationary_block3():
         assert ((logits > 0) != (logit_ref > 0)).mean() <= MAX_FLIP
 
 
+@pytest.mark.parametrize("h,w,n_streams,fps,gamma", [(45, 80, 2, 21, 1), (45, 80, 3, 23, 3), (33, 47, 1, 18, 2),
+                                                     (68, 120, 1, 9, 1), (135, 240, 1, 6, 1)])
+def test_fused_block1_equals_two_kernel_path(h, w, n_streams, fps, gamma):
+    """Block 1 as ONE kernel (frame-level conv + PointWiseTN over a register ring of frames, chains cut into frame
+    segments with 3 warm-up frames) must write exactly the bytes of the conv-per-frame + gather pair (debug bit 4):
+    X1, the t = 0 skip inside the decoder concat buffer, and therefore the logits."""
+    wts = weights.random_weights(7, head_bias=-1.0)
+    wts["enc0.bn_gamma"][::5] = -wts["enc0.bn_gamma"][::5]            # exercise the min-pool branch too
+    frames = synth.synth_streams(n_streams, fps, h, w, config_idx=8)
+    got = []
+    for dbg in (0, 16):
+        p = BlobPipeline(w, h, weights.to_blob(wts), n_streams, fps, gamma=gamma, keep_logits=True)
+        p.set_debug(dbg)
+        p.process(frames)
+        got.append((p.read_activation(1), p.read_activation(7), p.read_logits(), p.launch_count()))
+    assert got[0][3] + 1 == got[1][3]
+    for a, b in zip(got[0][:3], got[1][:3]):
+        assert a.shape == b.shape and (a == b).all()
+
+
 def test_gamma_subsampling_and_chain_restart():
     wts = weights.random_weights(0, head_bias=-1.0)
     frames = synth.synth_streams(2, 11, 45, 80, config_idx=3)
@@ -217,7 +237,7 @@ def test_pipeline_is_deterministic_and_reusable():
     b = synth.synth_streams(2, 7, 45, 80, config_idx=5)
     ra1, rb, ra2 = p.process(a), p.process(b), p.process(a)
     assert ra1 == ra2 and len(rb) == 2 * 4
-    assert p.launch_count() == 3 * 11        # tensorise, conv1, TN gather, 7 layer kernels, CCL
+    assert p.launch_count() == 3 * 10        # tensorise, fused block 1, 7 layer kernels, CCL
 
 
 def test_byte3_and_values_above_six_do_not_matter():

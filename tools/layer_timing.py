@@ -13,7 +13,7 @@ p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)
 p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
 p.set_profiling(True)
 res = {}
-for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither", 3), ("old_enc", 4)):
+for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither", 3), ("old_enc", 4), ("unfused_enc1", 16)):
     p.set_debug(flags)
     acc = {}
     for _ in range(4):
@@ -21,8 +21,8 @@ for name, flags in (("normal", 0), ("no_epilogue", 2), ("no_mma", 1), ("neither"
         for k, v in p.last_timings().items():
             acc.setdefault(k, []).append(v)
     res[name] = {k: float(np.mean(v[1:])) for k, v in acc.items()}
-keys = list(res["normal"])
+keys = list(dict.fromkeys(k for r in res.values() for k in r))
 print(f"{'kernel':16s}" + "".join(f"{n:>14s}" for n in res))
 for k in keys:
-    print(f"{k:16s}" + "".join(f"{res[n][k]:14.4f}" for n in res))
+    print(f"{k:16s}" + "".join(f"{res[n].get(k, 0.0):14.4f}" for n in res))
 print(f"{'total':16s}" + "".join(f"{sum(res[n].values()):14.4f}" for n in res), " windows", p.n_windows)
