@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcova_b200.so")
 
 OK, DROPPED = 0, 1
-E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE = -1, -2, -3, -4, -5, -6, -7
+E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE, E_NUMERIC = -1, -2, -3, -4, -5, -6, -7, -8
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED = 0x100, 0x200
 
@@ -75,6 +75,17 @@ SIGNATURES = {
     "cova_pipeline_launch_count": (ctypes.c_int, [_vp, _u64p]),
     "cova_pipeline_set_profiling": (ctypes.c_int, [_vp, ctypes.c_int]),
     "cova_pipeline_last_timings": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t, _f32p, _u32p]),
+    "cova_sorttracker_new": (ctypes.c_int, [_vpp]),
+    "cova_sorttracker_free": (None, [_vp]),
+    "cova_sorttracker_set_property": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_double]),
+    "cova_sorttracker_get_property": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "cova_sorttracker_set_caps": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_int32]),
+    "cova_sorttracker_transform": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_uint64, _vp, ctypes.c_size_t, _szp]),
+    "cova_sorttracker_eos": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp]),
+    "cova_sorttracker_n_tracks": (ctypes.c_int, [_vp, _u32p, _u32p]),
+    "cova_sort_linear_assignment": (ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _u32p]),
+    "cova_sort_iou_matrix": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
+    "cova_sort_match_dets": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, ctypes.c_float, _vp, _u32p]),
 }
 
 _lib = None

@@ -6,6 +6,8 @@ property names, caps arithmetic and flow results:
 
   MetaPreprocess   <- cova-rs/gst-plugins/src/metapreprocess/imp.rs  (properties timestep, gamma)
   BboxCc           <- cova-rs/gst-plugins/src/bboxcc/imp.rs          (property cc-threshold, default 30)
+  SortTracker      <- cova-rs/gst-plugins/src/sorttracker/imp.rs     (properties iou-threshold, maxage, minhits;
+                      host C++ behind the same C ABI, fed with the boxes the GPU path returns)
   BlobPipeline     <- the chain metapreprocess ! nvvideoconvert ! nvstreammux ! nvinfer(BlobNet) !
                       nvstreamdemux ! maskcopy ! bboxcc of pipeline/cova/pipeline.py:101-250, batched
                       over many chains, with only the bincode boxes returning to the host.
@@ -172,6 +174,89 @@ def deserialize_vec(buf: bytes) -> list[tuple]:
     if off != len(buf):
         raise ValueError("trailing bytes after Vec<Bbox>")
     return out
+
+
+def deserialize_vec_full(buf: bytes) -> list[tuple]:
+    """Bbox::deserialize_vec for boxes that may carry Some(track_id / timestamp / class_id / confidence):
+    (left, top, width, height, area, track_id, timestamp, class_id, confidence), None where absent."""
+    (n,) = struct.unpack_from("<Q", buf, 0)
+    out, off = [], 8
+    for _ in range(n):
+        vals = list(struct.unpack_from("<5f", buf, off))
+        off += 20
+        for fmt, size in (("<Q", 8), ("<Q", 8), ("<I", 4), ("<f", 4)):
+            tag = buf[off]
+            off += 1
+            if tag > 1:
+                raise ValueError("bad Option tag")
+            vals.append(struct.unpack_from(fmt, buf, off)[0] if tag else None)
+            off += size if tag else 0
+        out.append(tuple(vals))
+    if off != len(buf):
+        raise ValueError("trailing bytes after Vec<Bbox>")
+    return out
+
+
+class SortTracker:
+    """`sorttracker` element: per-frame bincode(Vec<Bbox>) in, bincode of the histories of the tracks that died on
+    this frame out; `eos()` is the extra buffer pushed on EOS (sorttracker/imp.rs:238-287)."""
+
+    ELEMENT_NAME = "sorttracker"
+    OUT_SIZE = 1 << 21  # transform_size(): constant 2 MiB (imp.rs:322-332)
+
+    def __init__(self, **props):
+        self._h = ctypes.c_void_p()
+        check(_lib.load().cova_sorttracker_new(ctypes.byref(self._h)))
+        self._out = np.empty(self.OUT_SIZE, dtype=np.uint8)
+        for k, v in props.items():
+            self.set_property(k.replace("_", "-"), v)
+
+    def set_property(self, name: str, value):
+        if name not in ("iou-threshold", "maxage", "minhits"):
+            raise KeyError(name)
+        check(_lib.load().cova_sorttracker_set_property(self._h, name.encode(), float(value)))
+
+    def get_property(self, name: str):
+        if name not in ("iou-threshold", "maxage", "minhits"):
+            raise KeyError(name)
+        v = ctypes.c_double()
+        check(_lib.load().cova_sorttracker_get_property(self._h, name.encode(), ctypes.byref(v)))
+        return v.value if name == "iou-threshold" else int(v.value)
+
+    def set_caps(self, width: int, height: int):
+        check(_lib.load().cova_sorttracker_set_caps(self._h, width, height))
+
+    def _call(self, fn, *args) -> bytes:
+        n = ctypes.c_size_t()
+        rc = fn(self._h, *args, _ptr(self._out), self._out.size, ctypes.byref(n))
+        if rc == _lib.E_TOOSMALL and fn is _lib.load().cova_sorttracker_eos:
+            self._out = np.empty(n.value, dtype=np.uint8)
+            rc = fn(self._h, *args, _ptr(self._out), self._out.size, ctypes.byref(n))
+        check(rc)
+        return self._out[: n.value].tobytes()
+
+    def transform(self, buf: bytes, pts_ns: int) -> bytes:
+        a = np.frombuffer(buf, dtype=np.uint8)
+        return self._call(_lib.load().cova_sorttracker_transform, _ptr(a), a.size, pts_ns)
+
+    def eos(self) -> bytes:
+        return self._call(_lib.load().cova_sorttracker_eos)
+
+    def n_tracks(self) -> tuple[int, int]:
+        t, a = ctypes.c_uint32(), ctypes.c_uint32()
+        check(_lib.load().cova_sorttracker_n_tracks(self._h, ctypes.byref(t), ctypes.byref(a)))
+        return t.value, a.value
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_sorttracker_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BlobPipeline:

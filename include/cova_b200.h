@@ -31,6 +31,7 @@ extern "C" {
 #define COVA_E_WEIGHTS (-5)     /* not a CVBN v1 weight container */
 #define COVA_E_UNSUPPORTED (-6) /* e.g. timestep != 4 for BlobNet, grid too large for the CCL kernel */
 #define COVA_E_NODEVICE (-7)    /* no CUDA device: there is no CPU fallback */
+#define COVA_E_NUMERIC (-8)     /* host tracker: Kalman innovation covariance not positive definite */
 
 const char *cova_version(void);
 const char *cova_strerror(int code);
@@ -165,6 +166,43 @@ int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count);
  * ';'-separated list, ms has one entry per name.  enable != 0 records CUDA events around every kernel. */
 int cova_pipeline_set_profiling(cova_pipeline *p, int enable);
 int cova_pipeline_last_timings(cova_pipeline *p, char *names, size_t names_cap, float *ms, uint32_t *n);
+
+/* ------------------------------------------------------------------------------------------------
+ * sorttracker element   (cova-rs/gst-plugins/src/sorttracker/imp.rs)
+ * The step AFTER the GPU path: host C++ (no CUDA), consumes the per-frame bincode(Vec<Bbox>) blobs that
+ * cova_pipeline_collect_host / cova_bboxcc_transform_ip produce and returns the histories of the tracks that
+ * died on this frame.
+ *   properties iou-threshold f32 [0,1] default 0.1, maxage u32 default 30, minhits u32 default 30, all
+ *     mutable while PLAYING but read only when caps are set                      imp.rs:10-12,53-137,214-236
+ *   set_caps(): (re)creates the Sort state                                       imp.rs:214-236
+ *   transform(): Bbox::deserialize_vec -> Sort::update(boxes, pts ns) -> bincode of the dead tracks'
+ *     histories, flattened in tracker order                                      imp.rs:238-266
+ *   EOS: Sort::finalize() -> one extra buffer                                    imp.rs:268-287
+ * Tracker semantics: cova-rs/sort/src/lib.rs:25-213, tracker/mod.rs:33-153, state.rs:10-27.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_sorttracker cova_sorttracker;
+
+int cova_sorttracker_new(cova_sorttracker **out);
+void cova_sorttracker_free(cova_sorttracker *s);
+/* GObject-style properties by name ("iou-threshold", "maxage", "minhits") */
+int cova_sorttracker_set_property(cova_sorttracker *s, const char *name, double value);
+int cova_sorttracker_get_property(const cova_sorttracker *s, const char *name, double *value);
+int cova_sorttracker_set_caps(cova_sorttracker *s, int32_t width, int32_t height);
+/* COVA_E_TOOSMALL reports the required size in *out_len; the tracker state has advanced regardless, so size
+ * the buffer like the element does (transform_size: 2 MiB, imp.rs:322-332) */
+int cova_sorttracker_transform(cova_sorttracker *s, const uint8_t *boxes, size_t boxes_len, uint64_t pts_ns,
+                               uint8_t *out, size_t out_cap, size_t *out_len);
+/* sink_event(EOS).  On COVA_E_TOOSMALL nothing is consumed and the call can be repeated. */
+int cova_sorttracker_eos(cova_sorttracker *s, uint8_t *out, size_t out_cap, size_t *out_len);
+int cova_sorttracker_n_tracks(const cova_sorttracker *s, uint32_t *n_total, uint32_t *n_active);
+
+/* building blocks of Sort, exported so that the reference's unit tests (sort/src/lib.rs:230-408) can be replayed.
+ * boxes are float[n][4] = (left, top, width, height); matrices are row-major [n_trk][n_det]; pairs is
+ * int32[min(n_trk,n_det)][2] = (tracker, detection), sorted by tracker. */
+int cova_sort_linear_assignment(const float *cost, uint32_t n_trk, uint32_t n_det, int32_t *pairs, uint32_t *n_pairs);
+int cova_sort_iou_matrix(const float *preds, uint32_t n_preds, const float *dets, uint32_t n_dets, float *out);
+int cova_sort_match_dets(const float *preds, const uint8_t *active, uint32_t n_preds, const float *dets, uint32_t n_dets,
+                         float iou_threshold, int32_t *pairs, uint32_t *n_pairs);
 
 #ifdef __cplusplus
 }
