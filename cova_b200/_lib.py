@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcova_b200.so")
 
 OK, DROPPED = 0, 1
-E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE, E_NUMERIC = -1, -2, -3, -4, -5, -6, -7, -8
+E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE, E_NUMERIC, E_STATE = -1, -2, -3, -4, -5, -6, -7, -8, -9
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED = 0x100, 0x200
 
@@ -87,6 +87,25 @@ SIGNATURES = {
     "cova_sort_iou_matrix": (ctypes.c_int, [_vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _vp]),
     "cova_sort_match_dets": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, ctypes.c_float, _vp, _u32p]),
 }
+
+
+
+class PushedBuffer(ctypes.Structure):
+    """cova_pushed_buffer"""
+    _fields_ = [("id", ctypes.c_uint64), ("pts_ns", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("list", ctypes.c_uint32)]
+
+
+SIGNATURES.update({
+    "cova_select_new": (ctypes.c_int, [_vpp]),
+    "cova_select_free": (None, [_vp]),
+    "cova_select_set_property": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_double]),
+    "cova_select_get_property": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
+    "cova_select_sink_enc": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]),
+    "cova_select_sink_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_uint64, _vp, ctypes.c_size_t, _szp]),
+    "cova_select_eos": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _szp]),
+    "cova_select_take_pushed": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp]),
+    "cova_select_take_wire": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp]),
+})
 
 _lib = None
 

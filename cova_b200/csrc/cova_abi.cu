@@ -58,6 +58,7 @@ extern "C" const char *cova_strerror(int code) {
         case COVA_E_UNSUPPORTED: return "unsupported configuration";
         case COVA_E_NODEVICE: return "no CUDA device (no CPU fallback)";
         case COVA_E_NUMERIC: return "numerical failure in the host tracker";
+        case COVA_E_STATE: return "inconsistent frame-selection state";
         default: return "unknown error";
     }
 }

@@ -5,6 +5,7 @@
 #include <new>
 
 #include "../../include/cova_b200.h"
+#include "cova_select.hpp"
 #include "sort_tracker.hpp"
 
 namespace cova {
@@ -136,5 +137,104 @@ extern "C" int cova_sort_match_dets(const float *preds, const uint8_t *active, u
     auto m = Sort::match_dets(p, a, d, iou_threshold);
     for (size_t i = 0; i < m.size(); i++) pairs[2 * i] = m[i].first, pairs[2 * i + 1] = m[i].second;
     *n_pairs = (uint32_t)m.size();
+    return COVA_OK;
+}
+
+// =================================================================================================
+// cova element: frame selection (cova_select.hpp)
+// =================================================================================================
+using cova::host::CovaSelect;
+using cova::host::Pushed;
+
+struct cova_select {
+    CovaSelect c;
+    std::vector<Pushed> pending;
+};
+
+static int take_pushed(cova_select *s, cova_pushed_buffer *out, size_t cap, size_t *n) {
+    if (n) *n = s->pending.size();
+    if (s->pending.size() > cap || (!out && !s->pending.empty()))
+        return fail(COVA_E_TOOSMALL, "pushed-buffer array too small; call cova_select_take_pushed with the reported count");
+    for (size_t i = 0; i < s->pending.size(); i++) {
+        out[i].id = s->pending[i].id, out[i].pts_ns = s->pending[i].pts;
+        out[i].flags = s->pending[i].flags, out[i].list = s->pending[i].list;
+    }
+    s->pending.clear();
+    return COVA_OK;
+}
+
+extern "C" int cova_select_new(cova_select **out) {
+    if (!out) return fail(COVA_E_INVAL, "null out");
+    cova_select *s = new (std::nothrow) cova_select();
+    if (!s) return fail(COVA_E_NOMEM, "host allocation failed");
+    *out = s;
+    return COVA_OK;
+}
+extern "C" void cova_select_free(cova_select *s) { delete s; }
+extern "C" int cova_select_set_property(cova_select *s, const char *name, double v) {
+    if (!s || !name) return fail(COVA_E_INVAL, "null argument");
+    const bool u32 = v >= 0.0 && v <= 4294967295.0;
+    if (!strcmp(name, "sort-iou")) {
+        if (!(v >= 0.0 && v <= 1.0)) return fail(COVA_E_INVAL, "sort-iou is a float in [0, 1]");
+        s->c.sort_iou = (float)v;
+    } else if (!strcmp(name, "sort-maxage") && u32) s->c.sort_maxage = (uint32_t)v;
+    else if (!strcmp(name, "sort-minhits") && u32) s->c.sort_minhits = (uint32_t)v;
+    else if (!strcmp(name, "port") && u32) s->c.port = (uint32_t)v;
+    else if (!strcmp(name, "alpha") && u32) s->c.alpha = (uint32_t)v;
+    else if (!strcmp(name, "beta") && u32) s->c.beta = (uint32_t)v;
+    else if (!strcmp(name, "infer-i")) s->c.infer_i = v != 0.0;
+    else if (!strcmp(name, "debug")) s->c.debug = v != 0.0;
+    else return fail(COVA_E_INVAL, "unknown or read-only property, or value out of range");
+    return COVA_OK;
+}
+extern "C" int cova_select_get_property(const cova_select *s, const char *name, double *v) {
+    if (!s || !name || !v) return fail(COVA_E_INVAL, "null argument");
+    if (!strcmp(name, "sort-iou")) *v = s->c.sort_iou;
+    else if (!strcmp(name, "sort-maxage")) *v = s->c.sort_maxage;
+    else if (!strcmp(name, "sort-minhits")) *v = s->c.sort_minhits;
+    else if (!strcmp(name, "port")) *v = s->c.port;
+    else if (!strcmp(name, "alpha")) *v = s->c.alpha;
+    else if (!strcmp(name, "beta")) *v = s->c.beta;
+    else if (!strcmp(name, "infer-i")) *v = s->c.infer_i;
+    else if (!strcmp(name, "debug")) *v = s->c.debug;
+    else if (!strcmp(name, "dropped")) *v = (double)s->c.dropped;
+    else if (!strcmp(name, "decoded-dependency")) *v = (double)s->c.decoded_dependency;
+    else if (!strcmp(name, "decoded-inference")) *v = (double)s->c.decoded_inference;
+    else return fail(COVA_E_INVAL, "unknown property");
+    return COVA_OK;
+}
+extern "C" int cova_select_sink_enc(cova_select *s, uint64_t buf_id, uint64_t pts_ns, uint32_t flags) {
+    if (!s) return fail(COVA_E_INVAL, "null handle");
+    if (!s->c.push_enc(buf_id, pts_ns, (flags & COVA_BUFFER_FLAG_DELTA_UNIT) != 0))
+        return fail(COVA_E_INVAL, "delta unit before the first key frame (the reference unwraps an empty GoP list)");
+    return COVA_OK;
+}
+extern "C" int cova_select_sink_mask(cova_select *s, const uint8_t *boxes, size_t boxes_len, uint64_t pts_ns,
+                                     cova_pushed_buffer *out, size_t out_cap, size_t *n_out) {
+    if (!s || !boxes) return fail(COVA_E_INVAL, "null argument");
+    std::vector<Bbox> dets;
+    if (!cova::host::decode_boxes(boxes, boxes_len, dets)) return fail(COVA_E_INVAL, "input is not bincode(Vec<Bbox>)");
+    const int rc = s->c.push_boxes(std::move(dets), pts_ns, s->pending);
+    if (rc == -1) return fail(COVA_E_NUMERIC, "Kalman update: innovation covariance not positive definite");
+    if (rc == -2) return fail(COVA_E_STATE, "no frame could be selected for a dead track (assert!(track_inferenced > 0), cova/imp.rs:239)");
+    return take_pushed(s, out, out_cap, n_out);
+}
+extern "C" int cova_select_eos(cova_select *s, int pad, cova_pushed_buffer *out, size_t out_cap, size_t *n_out) {
+    if (!s || (pad != 0 && pad != 1)) return fail(COVA_E_INVAL, "pad is 0 (sink_enc) or 1 (sink_mask)");
+    const bool drained = s->c.on_eos(pad, s->pending);
+    const int rc = take_pushed(s, out, out_cap, n_out);
+    if (rc) return rc;
+    return drained ? COVA_OK : COVA_DROPPED;
+}
+extern "C" int cova_select_take_pushed(cova_select *s, cova_pushed_buffer *out, size_t out_cap, size_t *n_out) {
+    if (!s) return fail(COVA_E_INVAL, "null handle");
+    return take_pushed(s, out, out_cap, n_out);
+}
+extern "C" int cova_select_take_wire(cova_select *s, uint8_t *out, size_t out_cap, size_t *out_len) {
+    if (!s) return fail(COVA_E_INVAL, "null handle");
+    if (out_len) *out_len = s->c.wire.size();
+    if (s->c.wire.size() > out_cap || (!out && !s->c.wire.empty())) return fail(COVA_E_TOOSMALL, "wire buffer too small");
+    if (!s->c.wire.empty()) memcpy(out, s->c.wire.data(), s->c.wire.size());
+    s->c.wire.clear();
     return COVA_OK;
 }

@@ -8,6 +8,8 @@ property names, caps arithmetic and flow results:
   BboxCc           <- cova-rs/gst-plugins/src/bboxcc/imp.rs          (property cc-threshold, default 30)
   SortTracker      <- cova-rs/gst-plugins/src/sorttracker/imp.rs     (properties iou-threshold, maxage, minhits;
                       host C++ behind the same C ABI, fed with the boxes the GPU path returns)
+  CovaSelect       <- cova-rs/gst-plugins/src/cova/imp.rs            (frame selection: which encoded frames still
+                      need a pixel decode; properties sort-iou, sort-maxage, sort-minhits, port, infer-i, alpha, beta)
   BlobPipeline     <- the chain metapreprocess ! nvvideoconvert ! nvstreammux ! nvinfer(BlobNet) !
                       nvstreamdemux ! maskcopy ! bboxcc of pipeline/cova/pipeline.py:101-250, batched
                       over many chains, with only the bincode boxes returning to the host.
@@ -250,6 +252,75 @@ class SortTracker:
     def close(self):
         if self._h:
             _lib.load().cova_sorttracker_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CovaSelect:
+    """`cova` element: `sink_enc(id, pts, flags)` for every encoded frame, `sink_mask(boxes, pts)` for every box
+    blob; both return / accumulate the buffer lists the element would push downstream as tuples
+    (id, pts, flags, list index)."""
+
+    ELEMENT_NAME = "cova"
+    FLAG_DELTA_UNIT, FLAG_DISCONT, FLAG_DROPPABLE = 1, 2, 4
+    EMPTY_LIST = 2**64 - 1
+
+    def __init__(self, **props):
+        self._h = ctypes.c_void_p()
+        check(_lib.load().cova_select_new(ctypes.byref(self._h)))
+        self._out = (_lib.PushedBuffer * 4096)()
+        for k, v in props.items():
+            self.set_property(k.replace("_", "-"), v)
+
+    def set_property(self, name: str, value):
+        check(_lib.load().cova_select_set_property(self._h, name.encode(), float(value)))
+
+    def get_property(self, name: str):
+        v = ctypes.c_double()
+        check(_lib.load().cova_select_get_property(self._h, name.encode(), ctypes.byref(v)))
+        return v.value if name == "sort-iou" else (bool(v.value) if name in ("infer-i", "debug") else int(v.value))
+
+    def sink_enc(self, buf_id: int, pts_ns: int, flags: int):
+        check(_lib.load().cova_select_sink_enc(self._h, buf_id, pts_ns, flags))
+
+    def _pushed(self, rc: int, n) -> list[tuple]:
+        if rc == _lib.E_TOOSMALL:
+            self._out = (_lib.PushedBuffer * n.value)()
+            rc = _lib.load().cova_select_take_pushed(self._h, self._out, len(self._out), ctypes.byref(n))
+        check(rc)
+        return [(b.id, b.pts_ns, b.flags, b.list) for b in self._out[: n.value]]
+
+    def sink_mask(self, boxes: bytes, pts_ns: int) -> list[tuple]:
+        a = np.frombuffer(boxes, dtype=np.uint8)
+        n = ctypes.c_size_t()
+        rc = _lib.load().cova_select_sink_mask(self._h, _ptr(a), a.size, pts_ns, self._out, len(self._out), ctypes.byref(n))
+        return self._pushed(rc, n)
+
+    def eos(self, pad: int):
+        """pad 0 = sink_enc, 1 = sink_mask; None until both pads have seen EOS."""
+        n = ctypes.c_size_t()
+        rc = _lib.load().cova_select_eos(self._h, pad, self._out, len(self._out), ctypes.byref(n))
+        out = self._pushed(rc, n)
+        return None if rc == _lib.DROPPED else out
+
+    def take_wire(self) -> bytes:
+        n = ctypes.c_size_t()
+        lib = _lib.load()
+        rc = lib.cova_select_take_wire(self._h, None, 0, ctypes.byref(n))
+        if rc == _lib.OK:
+            return b""
+        buf = np.empty(n.value, dtype=np.uint8)
+        check(lib.cova_select_take_wire(self._h, _ptr(buf), buf.size, ctypes.byref(n)))
+        return buf.tobytes()
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_select_free(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

@@ -32,6 +32,7 @@ extern "C" {
 #define COVA_E_UNSUPPORTED (-6) /* e.g. timestep != 4 for BlobNet, grid too large for the CCL kernel */
 #define COVA_E_NODEVICE (-7)    /* no CUDA device: there is no CPU fallback */
 #define COVA_E_NUMERIC (-8)     /* host tracker: Kalman innovation covariance not positive definite */
+#define COVA_E_STATE (-9)       /* host frame selection: a state the reference asserts can never happen */
 
 const char *cova_version(void);
 const char *cova_strerror(int code);
@@ -203,6 +204,50 @@ int cova_sort_linear_assignment(const float *cost, uint32_t n_trk, uint32_t n_de
 int cova_sort_iou_matrix(const float *preds, uint32_t n_preds, const float *dets, uint32_t n_dets, float *out);
 int cova_sort_match_dets(const float *preds, const uint8_t *active, uint32_t n_preds, const float *dets, uint32_t n_dets,
                          float iou_threshold, int32_t *pairs, uint32_t *n_pairs);
+
+/* ------------------------------------------------------------------------------------------------
+ * cova element: frame selection   (cova-rs/gst-plugins/src/cova/imp.rs, cova/tracker.rs)
+ * Two sink pads: sink_enc receives every ENCODED frame (kept per GoP), sink_mask the per-frame boxes of the
+ * blob-detection path.  The element tracks the boxes (SORT) and pushes, per GoP, the list of encoded frames a
+ * pixel decoder must still decode: the first frame at/after the start of every track that died unseen
+ * (counted as decoded-inference), preceded by the frames it depends on (flag DROPPABLE, decoded-dependency);
+ * everything else is dropped.  Host C++; buffers are referred to by a caller-chosen 64-bit id.
+ *   properties: sort-iou f32 0.1, sort-maxage u32 30, sort-minhits u32 30, port u32 0, infer-i bool false,
+ *     debug bool false, alpha u32 0, beta u32 0; read-only counters dropped, decoded-dependency,
+ *     decoded-inference (u64)                                                          imp.rs:22-56, 536-790
+ *   sink_enc chain: a buffer without DELTA_UNIT opens a GoP (its copy gets DISCONT)     imp.rs:292-331
+ *   sink_mask chain: Tracker::update -> selection -> GoPs older than 250 frames pushed  imp.rs:90-289
+ *   EOS on both pads: every GoP's list is pushed (even when empty), Tracker::flush      imp.rs:332-431
+ *   port != 0: dead / final tracks go to the aggregator as length-delimited (u32 BE) bincode
+ *     Frame{range_start, oldest, bboxes}; here the bytes are queued for cova_select_take_wire
+ *                                                              cova/tracker.rs:43-125, bbox/src/lib.rs:7-22
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_select cova_select;
+
+#define COVA_BUFFER_FLAG_DELTA_UNIT 1u /* gst::BufferFlags::DELTA_UNIT: not a key frame */
+#define COVA_BUFFER_FLAG_DISCONT 2u    /* set on the first frame of every GoP (imp.rs:305-307) */
+#define COVA_BUFFER_FLAG_DROPPABLE 4u  /* decode for reference only, no inference (imp.rs:186,211,221) */
+
+typedef struct cova_pushed_buffer {
+    uint64_t id;     /* the id given to cova_select_sink_enc; UINT64_MAX marks an EMPTY list pushed at EOS */
+    uint64_t pts_ns;
+    uint32_t flags;  /* COVA_BUFFER_FLAG_* */
+    uint32_t list;   /* index of the gst::BufferList within this call (one list per GoP) */
+} cova_pushed_buffer;
+
+int cova_select_new(cova_select **out);
+void cova_select_free(cova_select *s);
+int cova_select_set_property(cova_select *s, const char *name, double value);
+int cova_select_get_property(const cova_select *s, const char *name, double *value);
+int cova_select_sink_enc(cova_select *s, uint64_t buf_id, uint64_t pts_ns, uint32_t flags);
+/* On COVA_E_TOOSMALL the element state HAS advanced and *n_out is the number of entries waiting:
+ * fetch them with cova_select_take_pushed. */
+int cova_select_sink_mask(cova_select *s, const uint8_t *boxes, size_t boxes_len, uint64_t pts_ns,
+                          cova_pushed_buffer *out, size_t out_cap, size_t *n_out);
+/* pad: 0 = sink_enc, 1 = sink_mask.  COVA_DROPPED until both pads have seen EOS, COVA_OK when drained. */
+int cova_select_eos(cova_select *s, int pad, cova_pushed_buffer *out, size_t out_cap, size_t *n_out);
+int cova_select_take_pushed(cova_select *s, cova_pushed_buffer *out, size_t out_cap, size_t *n_out);
+int cova_select_take_wire(cova_select *s, uint8_t *out, size_t out_cap, size_t *out_len);
 
 #ifdef __cplusplus
 }
