@@ -95,7 +95,22 @@ class PushedBuffer(ctypes.Structure):
     _fields_ = [("id", ctypes.c_uint64), ("pts_ns", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("list", ctypes.c_uint32)]
 
 
+class Sample(ctypes.Structure):
+    """cova_sample"""
+    _fields_ = [("offset", ctypes.c_uint64), ("size", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+                ("dts", ctypes.c_uint64), ("pts", ctypes.c_uint64)]
+
+
+class Mp4Info(ctypes.Structure):
+    """cova_mp4_info"""
+    _fields_ = [("timescale", ctypes.c_uint32), ("width", ctypes.c_uint32), ("height", ctypes.c_uint32),
+                ("nal_length_size", ctypes.c_uint32)]
+
+
 SIGNATURES.update({
+    "cova_demux_mp4_samples": (ctypes.c_int, [_vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _szp, _vp]),
+    "cova_demux_annexb_frames": (ctypes.c_int, [_vp, ctypes.c_size_t, _vp, ctypes.c_size_t, _szp]),
+    "cova_gopsplit_ranges": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_uint32, _vp, _vp]),
     "cova_select_new": (ctypes.c_int, [_vpp]),
     "cova_select_free": (None, [_vp]),
     "cova_select_set_property": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_double]),

@@ -6,6 +6,7 @@
 
 #include "../../include/cova_b200.h"
 #include "cova_select.hpp"
+#include "gop_demux.hpp"
 #include "sort_tracker.hpp"
 
 namespace cova {
@@ -236,5 +237,40 @@ extern "C" int cova_select_take_wire(cova_select *s, uint8_t *out, size_t out_ca
     if (s->c.wire.size() > out_cap || (!out && !s->c.wire.empty())) return fail(COVA_E_TOOSMALL, "wire buffer too small");
     if (!s->c.wire.empty()) memcpy(out, s->c.wire.data(), s->c.wire.size());
     s->c.wire.clear();
+    return COVA_OK;
+}
+
+// =================================================================================================
+// demux + gopsplit (gop_demux.hpp)
+// =================================================================================================
+static int emit_samples(const std::vector<cova::host::Sample> &v, cova_sample *out, size_t cap, size_t *n) {
+    if (n) *n = v.size();
+    if (v.size() > cap || (!out && !v.empty())) return fail(COVA_E_TOOSMALL, "sample array too small");
+    for (size_t i = 0; i < v.size(); i++) {
+        out[i].offset = v[i].offset, out[i].size = v[i].size, out[i].flags = v[i].flags;
+        out[i].dts = v[i].dts, out[i].pts = v[i].pts;
+    }
+    return COVA_OK;
+}
+extern "C" int cova_demux_mp4_samples(const uint8_t *data, size_t len, cova_sample *out, size_t out_cap, size_t *n_out,
+                                      cova_mp4_info *info) {
+    if (!data) return fail(COVA_E_INVAL, "null argument");
+    std::vector<cova::host::Sample> v;
+    cova::host::Mp4Info mi;
+    const int rc = cova::host::mp4_video_samples(data, len, v, mi);
+    if (rc == -1) return fail(COVA_E_INVAL, "malformed or truncated ISO media file (moov / stbl)");
+    if (rc == -2) return fail(COVA_E_UNSUPPORTED, "no video track with an avc1 sample entry");
+    if (info) info->timescale = mi.timescale, info->width = mi.width, info->height = mi.height, info->nal_length_size = mi.nal_length_size;
+    return emit_samples(v, out, out_cap, n_out);
+}
+extern "C" int cova_demux_annexb_frames(const uint8_t *data, size_t len, cova_sample *out, size_t out_cap, size_t *n_out) {
+    if (!data && len) return fail(COVA_E_INVAL, "null argument");
+    std::vector<cova::host::Sample> v;
+    cova::host::annexb_frames(data, len, v);
+    return emit_samples(v, out, out_cap, n_out);
+}
+extern "C" int cova_gopsplit_ranges(const uint32_t *flags, size_t n_frames, uint32_t n_pads, uint64_t *first_frame, uint64_t *end_frame) {
+    if ((!flags && n_frames) || !first_frame || !end_frame) return fail(COVA_E_INVAL, "null argument");
+    if (!cova::host::gopsplit_ranges(flags, n_frames, n_pads, first_frame, end_frame)) return fail(COVA_E_INVAL, "there are no pads");
     return COVA_OK;
 }

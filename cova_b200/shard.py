@@ -15,6 +15,8 @@ def gop_ranges(n_gops: int, n_pads: int) -> list[tuple[int, int]]:
     """[start, end) GoP range of every pad, exactly as gopsplit assigns them."""
     if n_pads < 1:
         raise ValueError("there are no pads")
+    if n_gops < n_pads:                     # "Too many pads": pad i pushes GoP i (gstgopsplit.cpp:531-553)
+        return [(i, i + 1) if i < n_gops else (0, 0) for i in range(n_pads)]
     per = n_gops // n_pads
     out = []
     for i in range(n_pads):
@@ -26,8 +28,59 @@ def gop_ranges(n_gops: int, n_pads: int) -> list[tuple[int, int]]:
 
 
 def gop_starts(is_keyframe: list[bool]) -> list[int]:
-    """Frame index at which every GoP starts (a buffer without DELTA_UNIT; gstgopsplit.cpp:712-723)."""
-    return [i for i, k in enumerate(is_keyframe) if k]
+    """Frame index at which every GoP starts (a buffer without DELTA_UNIT; gstgopsplit.cpp:712-723).  Delta
+    frames ahead of the first key frame form a GoP of their own."""
+    return [i for i, k in enumerate(is_keyframe) if k or i == 0]
+
+
+def demux_mp4(data: bytes):
+    """(samples, info) of the first H.264 track: samples = list of (offset, size, is_key, dts, pts)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    lib = _lib.load()
+    a = np.frombuffer(data, dtype=np.uint8)
+    n, info = ctypes.c_size_t(), _lib.Mp4Info()
+    rc = lib.cova_demux_mp4_samples(a.ctypes.data, a.size, None, 0, ctypes.byref(n), ctypes.byref(info))
+    if rc not in (_lib.OK, _lib.E_TOOSMALL):
+        _lib.check(rc)
+    out = (_lib.Sample * max(1, n.value))()
+    _lib.check(lib.cova_demux_mp4_samples(a.ctypes.data, a.size, out, n.value, ctypes.byref(n), ctypes.byref(info)))
+    return ([(s.offset, s.size, not s.flags & 1, s.dts, s.pts) for s in out[: n.value]],
+            dict(timescale=info.timescale, width=info.width, height=info.height, nal_length_size=info.nal_length_size))
+
+
+def demux_annexb(data: bytes):
+    """Access units of an Annex-B stream: list of (offset, size, is_key)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    lib = _lib.load()
+    a = np.frombuffer(data, dtype=np.uint8)
+    n = ctypes.c_size_t()
+    rc = lib.cova_demux_annexb_frames(a.ctypes.data, a.size, None, 0, ctypes.byref(n))
+    if rc not in (_lib.OK, _lib.E_TOOSMALL):
+        _lib.check(rc)
+    out = (_lib.Sample * max(1, n.value))()
+    _lib.check(lib.cova_demux_annexb_frames(a.ctypes.data, a.size, out, n.value, ctypes.byref(n)))
+    return [(s.offset, s.size, not s.flags & 1) for s in out[: n.value]]
+
+
+def gopsplit_ranges(is_keyframe, n_pads: int) -> list[tuple[int, int]]:
+    """[first_frame, end_frame) per pad, computed by the native library (cova_gopsplit_ranges)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    flags = np.array([0 if k else 1 for k in is_keyframe], dtype=np.uint32)
+    first, end = np.zeros(n_pads, dtype=np.uint64), np.zeros(n_pads, dtype=np.uint64)
+    _lib.check(_lib.load().cova_gopsplit_ranges(flags.ctypes.data, flags.size, n_pads, first.ctypes.data, end.ctypes.data))
+    return [(int(a), int(b)) for a, b in zip(first, end)]
 
 
 def frames_of_shard(is_keyframe: list[bool], n_pads: int, pad: int) -> tuple[int, int]:

@@ -249,6 +249,32 @@ int cova_select_eos(cova_select *s, int pad, cova_pushed_buffer *out, size_t out
 int cova_select_take_pushed(cova_select *s, cova_pushed_buffer *out, size_t out_cap, size_t *n_out);
 int cova_select_take_wire(cova_select *s, uint8_t *out, size_t out_cap, size_t *out_len);
 
+/* ------------------------------------------------------------------------------------------------
+ * demux + gopsplit   (gst-plugins/gst-gopsplit/gstgopsplit.cpp:500-729, pipeline/cova/pipeline.py:60-92;
+ * SURVEY 8f row f4).  Host C++.  Finds the frames and key frames of a stream the way the front of the reference
+ * pipeline (filesrc ! qtdemux ! h264parse) labels them, and cuts them into per-pad (= per-GPU) runs of whole GoPs
+ * exactly as gopsplit assigns them: floor(G/P) GoPs per pad, the remainder to the last pad; with fewer GoPs than pads,
+ * pad i gets GoP i.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cova_sample {
+    uint64_t offset; /* byte offset of the frame in the input */
+    uint32_t size;
+    uint32_t flags;  /* COVA_BUFFER_FLAG_DELTA_UNIT unless the frame is a key frame */
+    uint64_t dts, pts; /* MP4: track timescale units; Annex B: frame index */
+} cova_sample;
+typedef struct cova_mp4_info {
+    uint32_t timescale, width, height, nal_length_size;
+} cova_mp4_info;
+
+/* sample table of the first H.264 video track of an ISO media file (the whole file, or at least its moov box);
+ * key frames = the stss sync samples, like qtdemux */
+int cova_demux_mp4_samples(const uint8_t *data, size_t len, cova_sample *out, size_t out_cap, size_t *n_out,
+                           cova_mp4_info *info);
+/* access units of an Annex-B byte stream; key frames = units holding an IDR slice, like h264parse */
+int cova_demux_annexb_frames(const uint8_t *data, size_t len, cova_sample *out, size_t out_cap, size_t *n_out);
+/* flags[n_frames] as above -> [first_frame[p], end_frame[p]) for every pad p (empty range = 0, 0) */
+int cova_gopsplit_ranges(const uint32_t *flags, size_t n_frames, uint32_t n_pads, uint64_t *first_frame, uint64_t *end_frame);
+
 #ifdef __cplusplus
 }
 #endif

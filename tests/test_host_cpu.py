@@ -72,7 +72,8 @@ def test_flops_per_window_match_survey():
 
 def test_gopsplit_ranges_remainder_to_last_pad():
     assert shard.gop_ranges(8, 3) == [(0, 2), (2, 4), (4, 8)]
-    assert shard.gop_ranges(7, 8)[-1] == (0, 7) and shard.gop_ranges(7, 8)[0] == (0, 0)
+    # fewer GoPs than pads: pad i pushes GoP i, the other pads nothing (gstgopsplit.cpp:531-553)
+    assert shard.gop_ranges(7, 8) == [(i, i + 1) for i in range(7)] + [(0, 0)]
     key = [i % 250 == 0 for i in range(1802)]              # demo/1m.mp4: 1802 frames, 8 key frames
     spans = [shard.frames_of_shard(key, 4, p) for p in range(4)]
     assert spans == [(0, 500), (500, 1000), (1000, 1500), (1500, 1802)]
