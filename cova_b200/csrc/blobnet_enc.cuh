@@ -78,6 +78,9 @@ struct ECfg {
     static constexpr int MAXU = UB + (UR ? 1 : 0);
     static constexpr int NIT = 4 / PL;                     // (channel block) items per thread and group
     static constexpr int CBQ = COUT / 32;                  // output channel blocks per TMEM lane quarter (= NIT)
+    // Block 4 (Cout = 128) is the last encoder block: it has no next-encoder output, only the t = 0 skip row of the
+    // decoder input; blocks 2 and 3 always write both.  Compile-time, so the finalisation carries no pointer tests.
+    static constexpr bool HAS_OUT = COUT < 128;
     static_assert(COUT * PL == 128, "M = 128 rows = lane phases x output channels");
     static_assert(CIN_CB % 2 == 0, "a K = 16 step spans two channel blocks");
     static_assert(NP % 16 == 0 && NP >= 16 && NP <= 256, "N of one MMA");
@@ -177,6 +180,12 @@ __device__ __forceinline__ void pool_unit(const uint32_t (&a0)[8], const uint32_
         }
 }
 
+// 2-byte store to a global address held as an opaque 64-bit value (see the asm barrier on outb / out2b in the kernel)
+template <int OFF>
+__device__ __forceinline__ void stg_h(const unsigned char *addr, float v) {
+    asm volatile("st.global.b16 [%0 + %2], %1;" ::"l"(addr), "h"(__half_as_ushort(__float2half_rn(v))), "n"(OFF) : "memory");
+}
+
 struct EpiItem {
     float sgn, bias, scale, shift;
 };
@@ -185,11 +194,12 @@ struct EpiItem {
 // all four frames of ONE pixel (th = 0: pixel of block 0, th = 1: pixel of block 1); then bias -> ReLU -> BatchNorm,
 // PointWiseTN over the 4 frames entirely in registers (packed fp32 pairs, TN weights straight from the kernel
 // parameters), fp16, store.  All lanes must call (shuffles); stores are predicated.
-// orow / srow: 16-byte row index of (channel block 0, this thread's pixel, t = 0) in out / out2.
+// orow / srow: 16-byte row index of (channel block 0, this thread's pixel, t = 0) in out / out2;
+// outb / out2b: byte address of this thread's channel inside row 0 of out / out2.
 template <class C>
 __device__ __forceinline__ void finalize_unit(const LayerParams &p, const float (&v)[C::NIT][4], const EpiItem (&ecr)[C::NIT],
-                                              const float4 *ecs, bool th,
-                                              bool valid, uint32_t orow, uint32_t srow, uint32_t step_o, uint32_t step_s, uint32_t jch) {
+                                              const float4 *ecs, bool th, bool valid, unsigned char *outb, unsigned char *out2b,
+                                              uint32_t orow, uint32_t srow, uint32_t step_o, uint32_t step_s) {
 #pragma unroll
     for (int it = 0; it < C::NIT; it++) {
         // th = 0 keeps block 0 (frames 0,1 of its pixel) and receives frames 2,3 of it from the partner's block 0;
@@ -219,18 +229,18 @@ __device__ __forceinline__ void finalize_unit(const LayerParams &p, const float 
         y01 = ffma2(bc2(h23.x), make_float2(p.tn_w2[8], p.tn_w2[9]), y01);
         y01 = ffma2(bc2(h23.y), make_float2(p.tn_w2[12], p.tn_w2[13]), y01);
         const float o0 = fmax3(y01.x, x01.x, 0.f), o1 = fmax3(y01.y, x01.y, 0.f);
-        if (p.out) {
+        if constexpr (C::HAS_OUT) {
             float2 y23 = ffma2(bc2(h01.x), make_float2(p.tn_w2[2], p.tn_w2[3]), x23);
             y23 = ffma2(bc2(h01.y), make_float2(p.tn_w2[6], p.tn_w2[7]), y23);
             y23 = ffma2(bc2(h23.x), make_float2(p.tn_w2[10], p.tn_w2[11]), y23);
             y23 = ffma2(bc2(h23.y), make_float2(p.tn_w2[14], p.tn_w2[15]), y23);
             const float o2 = fmax3(y23.x, x23.x, 0.f), o3 = fmax3(y23.y, x23.y, 0.f);
             if (valid) {
-                __half *dst = reinterpret_cast<__half *>(p.out) + ((size_t)(orow + (uint32_t)it * step_o) * 8 + jch);
-                dst[0] = __float2half_rn(o0); dst[8] = __float2half_rn(o1); dst[16] = __float2half_rn(o2); dst[24] = __float2half_rn(o3);
+                const unsigned char *dst = outb + (size_t)(orow + (uint32_t)it * step_o) * 16;     // rows t = 0..3 are consecutive
+                stg_h<0>(dst, o0); stg_h<16>(dst, o1); stg_h<32>(dst, o2); stg_h<48>(dst, o3);
             }
         }
-        if (valid && p.out2) reinterpret_cast<__half *>(p.out2)[(size_t)(srow + (uint32_t)it * step_s) * 8 + jch] = __float2half_rn(o0);
+        if (valid) stg_h<0>(out2b + (size_t)(srow + (uint32_t)it * step_s) * 16, o0);
     }
 }
 
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
+    pdl_launch_dependents();
 
     for (int i = threadIdx.x; i < 4 * C::COUT + 32; i += C::THREADS) {
         float v;
@@ -282,6 +293,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    pdl_wait();              // prologue done (weights in TMEM); activations of the preceding layer from here on
 
     if (warp == 0) {
         // ===== producer: one strip set per group of TPS tiles =====
@@ -339,6 +351,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
         const uint32_t step_o = 4u * (uint32_t)p.gout.Lp, step_s = 4u * (uint32_t)p.gout2.Lp;
         const uint32_t base_o = (uint32_t)(q * C::NIT) * step_o + (uint32_t)p.gout.guard;
         const uint32_t base_s = (uint32_t)(p.out2_cb + q * C::NIT) * step_s + (uint32_t)p.gout2.guard;
+        unsigned char *outb = reinterpret_cast<unsigned char *>(p.out) + jch * 2u;
+        unsigned char *out2b = reinterpret_cast<unsigned char *>(p.out2) + jch * 2u;
+        asm volatile("" : "+l"(outb), "+l"(out2b));          // keep both in registers: ptxas otherwise re-derives them per unit
         // Software pipeline over this CTA's tiles: the accumulators of tile i+1 are read (and the slot released) pass by
         // pass as they complete, interleaved with the finalisation of tile i out of registers - so the MMA warp never
         // waits for a finalisation and the epilogue never waits for a pass it could have had earlier.
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
             return -1;
         };
         float run_cur[C::MAXU][C::NIT][4];
-        uint32_t cur_o = 0, cur_s = 0, cur_vmask = 0;
+        uint32_t cur_o = 0, cur_s = 0, cur_vmask = 0, cur_vmine = 0;   // cur_vmine: validity bits of this thread's pixel of every unit
         bool have_cur = false;
         int tile = next_tile();
         while (tile >= 0 || have_cur) {
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
                         if (u >= u_lo && u < u_hi && u < n_my && ((cur_vmask >> (4 * u)) & 15u)) {   // warp-uniform: skip padding units
                             const uint32_t orow = __shfl_sync(0xffffffffu, cur_o, 4 * u + pix_in_unit);
                             const uint32_t srow = __shfl_sync(0xffffffffu, cur_s, 4 * u + pix_in_unit);
-                            finalize_unit<C>(p, run_cur[u], ec, ecs, th, (cur_vmask >> (4 * u + pix_in_unit)) & 1u, orow, srow, step_o, step_s, jch);
+                            finalize_unit<C>(p, run_cur[u], ec, ecs, th, (cur_vmine & (1u << (4 * u))) != 0u, outb, out2b, orow, srow, step_o, step_s);
                         }
                 }
             }
@@ -436,7 +451,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
                     for (int it = 0; it < C::NIT; it++)
 #pragma unroll
                         for (int c = 0; c < 4; c++) run_cur[u][it][c] = run_nxt[u][it][c];
-                cur_o = nxt_o; cur_s = nxt_s; cur_vmask = nxt_vmask;
+                cur_o = nxt_o; cur_s = nxt_s; cur_vmask = nxt_vmask; cur_vmine = nxt_vmask >> pix_in_unit;
                 tile = next_tile();
             }
         }
@@ -451,6 +466,7 @@ template <class C>
 inline bool try_launch_e(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &err, int min_stage) {
     const long long mtot = (long long)p.N * p.gin.S * p.gin.Tn;
     if (mtot >= (1ll << 31)) return false;
+    if ((p.out != nullptr) != C::HAS_OUT || !p.out2) return false;       // output set is part of the configuration (ECfg::HAS_OUT)
     p.n_tiles = (int)((mtot + C::NP - 1) / C::NP);
     p.n_groups = (p.n_tiles + C::TPS - 1) / C::TPS;
     p.Ls = C::TPS * C::NP + 2 * p.gin.halo;
@@ -467,8 +483,7 @@ inline bool try_launch_e(LayerParams p, int n_sms, cudaStream_t st, cudaError_t 
     ex.divP = make_fastdiv((uint32_t)p.gin.P);
     int ctas = std::min(n_sms, p.n_groups);
     if (ctas < 1) ctas = 1;
-    enc_ws_kernel<C><<<ctas, C::THREADS, sp.total, st>>>(p, ex);
-    err = cudaGetLastError();
+    err = launch_pdl(enc_ws_kernel<C>, dim3((unsigned)ctas), dim3(C::THREADS), sp.total, st, p, ex);
     return true;
 }
 

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = (int)blockIdx.x, n_cta = (int)gridDim.x;
+    pdl_launch_dependents();
 
     for (int i = threadIdx.x; i < 3 * 16; i += kThreads1) epi[i] = p.epi[i];     // bias | scale | shift
     if (threadIdx.x == 0) {
@@ -98,12 +99,16 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0 && tc::elect_one()) {          // weights do not depend on the preceding kernel: fetch them before the wait
+        tc::mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
+        tc::bulk_g2s(smem_base + sp.w_off, p.wpack, (uint32_t)p.w_bytes, w_bar);
+    }
+    __syncwarp();
+    pdl_wait();
 
     if (warp == 0) {
-        // ===== producer: weights once, then the two row-parity strips of one frame per step =====
+        // ===== producer: the two row-parity strips of one frame per step =====
         if (tc::elect_one()) {
-            tc::mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
-            tc::bulk_g2s(smem_base + sp.w_off, p.wpack, (uint32_t)p.w_bytes, w_bar);
             uint32_t it = 0;
             for (int item = cta; item < ex.n_items; item += n_cta) {
                 const Item w = decode_item(ex, item);
@@ -274,8 +279,7 @@ inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t
     err = cudaFuncSetAttribute(enc1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
     if (err != cudaSuccess) return true;
     const int ctas = std::max(1, std::min(n_sms, ex.n_items));
-    enc1_fused_kernel<<<ctas, kThreads1, total, st>>>(p, ex);
-    err = cudaGetLastError();
+    err = launch_pdl(enc1_fused_kernel, dim3((unsigned)ctas), dim3(kThreads1), total, st, p, ex);
     return true;
 }
 

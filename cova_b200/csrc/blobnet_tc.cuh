@@ -47,6 +47,7 @@ struct LayerParams {
     unsigned int *watchdog;            // set to a non-zero code if a barrier wait times out
     int bn_nonneg;                     // ENC: every BatchNorm scale of the layer is >= 0 (skips the min-pool path)
     int dbg;                           // experiments only: bit0 = skip the MMAs, bit1 = skip the epilogue math (results are garbage)
+    int psplit;                        // DEC with 512 accumulator columns per tile: two half-tiles of two input phases each (see Cfg::CAN_SPLIT)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -152,6 +153,11 @@ struct Cfg {
     static constexpr int KP = ENCF ? 1 : KCH / 2;                        // K=16 steps per tap inside a stage
     static constexpr int BLOCKS = ENCF ? 6 : NTAP * (CIN_CB / 2);        // B blocks per N-half
     static constexpr int BLOCK_N = ENCF ? 4 * NCOLS : NCOLS;             // rows of one B block (= N of one MMA)
+    // A decoder tile whose four phase accumulators fill all 512 TMEM columns (dec0, dec1) cannot be double-buffered as a
+    // whole: its MMAs and its epilogue would alternate.  Such a tile is processed as two half-tiles (input phases 0,1 and
+    // 2,3; 256 columns each, own full/empty barriers): the strips pass through the stage ring once per half, and the
+    // epilogue of one half runs under the MMAs of the other.  Accumulation order per phase is unchanged (bit-identical).
+    static constexpr bool CAN_SPLIT = MODE == MODE_DEC && COLS_TILE == 512 && TPS == 1;
     static_assert(NKC == 1 || TPS == 1, "accumulating over k-chunks needs one tile per stage");
     static_assert(ENCF || (KCH % 2 == 0), "a K=16 step spans two channel blocks");
     static_assert(COLS_TILE <= 512, "accumulators exceed TMEM");
@@ -182,7 +188,7 @@ __host__ __device__ constexpr int epi_floats() {
 // ------------------------------------------------------------------------------------------------ MMA issue
 // All MMAs of one tile for one stage (k-chunk kc).  Fully unrolled: plane/shift of every tap are
 // compile-time, only P, Tn, Ls are runtime.
-template <class C>
+template <class C, int PH0 = 0, int NPH = 4>
 __device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_addr, uint32_t w_addr, uint32_t d_tmem,
                                            int tile_in_stage, int kc, uint32_t idesc) {
     const int Ls = p.Ls, P = p.gin.P, Tn = p.gin.Tn;
@@ -206,7 +212,7 @@ __device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_
         const uint32_t a_lbo = (uint32_t)(4 * Ls * 16);
         const uint64_t bdesc0 = make_desc(w_addr, (uint32_t)C::NCOLS * 16u, 128u);
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) {
+        for (int ph = PH0; ph < PH0 + NPH; ph++) {
             const int pa = ph >> 1, pb = ph & 1;
             const uint32_t d = d_tmem + (uint32_t)(ph * C::NCOLS);
 #pragma unroll
@@ -464,6 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
     const int half = (int)blockIdx.x % nsplit;
     const int cta = (int)blockIdx.x / nsplit, n_cta = (int)gridDim.x / nsplit;
+    int nh = 1;                                   // half-tiles per tile
+    if constexpr (C::CAN_SPLIT) nh = p.psplit ? 2 : 1;
+    pdl_launch_dependents();
 
     // epilogue constants -> smem (generic proxy)
     constexpr int kEpiConst = C::MODE == MODE_ENC ? 3 * C::COUT + 32 : epi_floats<C>();
@@ -475,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStage; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 8; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * C::CG); }
+        for (int s = 0; s < 8; s++) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * C::CG / nh); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
@@ -487,17 +496,21 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0 && elect_one()) {              // weights do not depend on the preceding kernel: fetch them before the wait
+        mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
+        bulk_g2s(smem_base + sp.w_off, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)half * p.w_bytes,
+                 (uint32_t)p.w_bytes, w_bar);
+    }
+    __syncwarp();
+    pdl_wait();
 
     if (warp == 0) {
-        // ===== producer: weights once, then one strip per (group, k-chunk) =====
+        // ===== producer: one strip per (group, k-chunk) =====
         if (elect_one()) {
-            mbar_expect_tx(w_bar, (uint32_t)p.w_bytes);
-            bulk_g2s(smem_base + sp.w_off, reinterpret_cast<const unsigned char *>(p.wpack) + (size_t)half * p.w_bytes,
-                     (uint32_t)p.w_bytes, w_bar);
             uint32_t it = 0;
             for (int g = cta; g < p.n_groups; g += n_cta) {
                 const long long pos0 = p.gin.guard + (long long)g * C::TPS * kTileM - p.gin.halo;
-                for (int kc = 0; kc < C::NKC; kc++, it++) {
+                for (int kc = 0; kc < C::NKC * nh; kc++, it++) {     // half-tiles: the k-chunks pass through the ring once per half
                     const int s = (int)(it % (uint32_t)p.n_stage);
                     mbar_wait(empty_bar(s), ((it / (uint32_t)p.n_stage) & 1u) ^ 1u, p.watchdog, 1u);
                     mbar_expect_tx(full_bar(s), sp.stage_bytes);
@@ -507,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
 #pragma unroll
                         for (int pl = 0; pl < C::NPLANE; pl++)
                             bulk_g2s(dst0 + (uint32_t)((cbi * C::NPLANE + pl) * p.Ls) * 16u,
-                                     p.in + geom_row(p.gin, kc * C::KCH + cbi, pl * (4 / C::NPLANE), pos0), (uint32_t)p.Ls * 16u, full_bar(s));
+                                     p.in + geom_row(p.gin, (kc % C::NKC) * C::KCH + cbi, pl * (4 / C::NPLANE), pos0), (uint32_t)p.Ls * 16u, full_bar(s));
                 }
             }
         }
@@ -519,6 +532,28 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
             uint32_t it = 0, tile_it = 0;
             for (int g = cta; g < p.n_groups; g += n_cta) {
                 const uint32_t tile_it0 = tile_it;
+                if constexpr (C::CAN_SPLIT) {
+                    if (nh == 2) {
+                        // two half-tiles (input phases 0,1 | 2,3), each with its own accumulator barriers
+                        for (int hh = 0; hh < 2; hh++) {
+                            for (int kc = 0; kc < C::NKC; kc++, it++) {
+                                const int s = (int)(it % (uint32_t)p.n_stage);
+                                mbar_wait(full_bar(s), (it / (uint32_t)p.n_stage) & 1u, p.watchdog, 3u);
+                                if (kc == 0) mbar_wait(tempty_bar(hh), (tile_it & 1u) ^ 1u, p.watchdog, 4u);
+                                tc_fence_after();
+                                const uint32_t stage_addr = smem_base + sp.stage_off + (uint32_t)s * sp.stage_bytes;
+                                if (!(p.dbg & 1)) {
+                                    if (hh == 0) issue_tile<C, 0, 2>(p, stage_addr, smem_base + sp.w_off, tmem_base, 0, kc, idesc);
+                                    else issue_tile<C, 2, 2>(p, stage_addr, smem_base + sp.w_off, tmem_base, 0, kc, idesc);
+                                }
+                                if (kc == C::NKC - 1) umma_commit(tfull_bar(hh));
+                                umma_commit(empty_bar(s));
+                            }
+                        }
+                        tile_it++;
+                        continue;
+                    }
+                }
                 for (int kc = 0; kc < C::NKC; kc++, it++) {
                     const int s = (int)(it % (uint32_t)p.n_stage);
                     mbar_wait(full_bar(s), (it / (uint32_t)p.n_stage) & 1u, p.watchdog, 3u);
@@ -554,10 +589,12 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                 const int tile = g * C::TPS + j;
                 if (tile >= p.n_tiles) break;
                 if ((int)(tile_it % (uint32_t)C::TG) == tg) {
-                    const int slot = (int)(tile_it % (uint32_t)C::NSLOT);
-                    mbar_wait(tfull_bar(slot), (tile_it / (uint32_t)C::NSLOT) & 1u, p.watchdog, 5u);
+                    int slot = (int)(tile_it % (uint32_t)C::NSLOT);
+                    uint32_t acc_col = (uint32_t)(slot * C::COLS_TILE);
+                    if (nh == 2) { slot = cg >> 1; acc_col = 0u; }                 // half-tile of this group's input phase
+                    mbar_wait(tfull_bar(slot), (nh == 2 ? tile_it : tile_it / (uint32_t)C::NSLOT) & 1u, p.watchdog, 5u);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * C::COLS_TILE);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col;
                     const int pp = tile * kTileM + q * 32 + lane;
                     if (p.dbg & 2) {
                     } else if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, scratch, taddr, pp, lane, cg);
@@ -601,8 +638,7 @@ inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &e
     int ctas = n_sms / nsplit;
     if (ctas > p.n_groups) ctas = p.n_groups;
     if (ctas < 1) ctas = 1;
-    shiftgemm_kernel<C><<<ctas * nsplit, kThreads, sp.total, st>>>(p);
-    err = cudaGetLastError();
+    err = launch_pdl(shiftgemm_kernel<C>, dim3((unsigned)(ctas * nsplit)), dim3(kThreads), sp.total, st, p);
     return true;
 }
 

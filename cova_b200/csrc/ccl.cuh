@@ -66,6 +66,8 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
 
     const int frame = blockIdx.x;
     const int tid = threadIdx.x, nt = blockDim.x;
+    pdl_launch_dependents();
+    pdl_wait();              // the mask comes from the preceding kernel of the stream (common.cuh, "Programmatic dependent launch")
     const uint8_t *m = A.masks + (size_t)frame * A.H * A.W;
 
     // 1. 2x2 block codes: bit0 (0,0) bit1 (0,1) bit2 (1,0) bit3 (1,1).  Horizontal runs are linked here, without
@@ -82,10 +84,12 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             const int y = 2 * by, x = 2 * bx;
             const uint8_t *r0 = m + (size_t)y * A.W + x;
             const bool x1 = x + 1 < A.W, y1 = y + 1 < A.H;
-            c = (__ldg(r0) != 0) ? 1 : 0;
-            if (x1 && __ldg(r0 + 1) != 0) c |= 2;
-            if (y1 && __ldg(r0 + A.W) != 0) c |= 4;
-            if (x1 && y1 && __ldg(r0 + A.W + 1) != 0) c |= 8;
+            // plain (coherent) loads: under programmatic dependent launch the mask is written while this grid is
+            // already resident, which rules out the read-only data path
+            c = (r0[0] != 0) ? 1 : 0;
+            if (x1 && r0[1] != 0) c |= 2;
+            if (y1 && r0[A.W] != 0) c |= 4;
+            if (x1 && y1 && r0[A.W + 1] != 0) c |= 8;
         }
         const int cw = __shfl_up_sync(0xffffffffu, c, 1);
         const bool west = lane > 0 && bx > 0 && (c & 0x5) && (cw & 0xA);       // my left column / its right column
@@ -209,7 +213,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     for (int p = tid; p < A.H * A.W; p += nt) {
         int y = p / A.W, x = p - y * A.W;
         int b = (y >> 1) * A.nbx + (x >> 1);
-        lab[p] = (__ldg(m + p) != 0) ? area[parent[b]] : 0;
+        lab[p] = (m[p] != 0) ? area[parent[b]] : 0;
     }
 }
 

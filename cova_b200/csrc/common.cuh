@@ -119,6 +119,33 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the path is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, fires `launch_dependents` on entry and executes
+// `pdl_wait()` (griddepcontrol.wait: the preceding kernel of the stream has completed and flushed) after its own
+// prologue (barrier init, TMEM allocation, weights -> shared memory / TMEM) and before it touches any activation
+// buffer.  A persistent CTA of layer k+1 therefore starts on an SM the moment layer k's CTA leaves it, and the
+// launch latency and prologue of k+1 hide behind the tail of k.  EVERY thread of EVERY kernel in the chain waits:
+// completion of k then implies completion of k-1, k-2, ... (buffers are re-used from step to step).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern bool g_pdl;   // development switch (cova_pipeline_set_debug bit 5 clears it): plain stream-ordered launches
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct alignas(16) Row8 {  // one 16-byte row: 8 fp16 channels
     __half v[8];
 };

@@ -17,6 +17,7 @@
 
 namespace cova {
 thread_local char g_err[512] = "";
+bool g_pdl = true;
 
 static int check_device(int device) {
     int n = 0;
@@ -223,8 +224,7 @@ static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_
     a.stats = want_labels ? b.d_stats : nullptr;
     a.n_labels = want_labels ? b.d_nlabels : nullptr;
     if (reset_cursor) COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
-    ccl_bbox_kernel<<<n, b.threads, b.smem, st>>>(a);
-    COVA_CUDA(cudaGetLastError());
+    COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, a));
     return COVA_OK;
 }
 
@@ -662,8 +662,8 @@ static int tensorise_chunk(cova_pipeline *p) {
         const int F = (int)(p->ck_n_streams * p->cur_fps);
         long long total = (long long)F * p->H * p->gx0f.Wh;
         int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
-        tensorise_frames_kernel<<<blocks, 256, 0, p->stream>>>(reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F);
-        COVA_CUDA(cudaGetLastError());
+        COVA_CUDA(launch_pdl(tensorise_frames_kernel, dim3((unsigned)blocks), dim3(256), 0, p->stream,
+                             reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F));
         p->launches++;
         prof_mark(p, "tensorise_frames");
     }
@@ -879,6 +879,7 @@ static int tc_layer(cova_pipeline *p, int layer) {
     lp.gout = i < 3 ? p->gd[i + 1] : p->gd[3];
     lp.wpack = p->dec[i].wpack; lp.epi = p->dec[i].epi;
     lp.nsplit = i == 0 ? 2 : 1;
+    lp.psplit = (p->dbg & 64) ? 0 : 1;     // dbg bit 6: whole-tile accumulators for dec0 / dec1 (experiments)
     lp.Ht = p->sizes_h[3 - i]; lp.Wt = p->sizes_w[3 - i];
     crop_for(lp.gin.H, lp.Ht, lp.crop_t);
     crop_for(lp.gin.W, lp.Wt, lp.crop_l);
@@ -951,9 +952,12 @@ static void prof_begin(cova_pipeline *p) {
 // all kernels of one chunk, on p->stream
 static int run_chunk(cova_pipeline *p, uint32_t c) {
     select_chunk(p, c);
+    // the box arena's cursor is reset ahead of the batch's first kernel, not between the last layer and the CCL
+    // kernel: a memset node there would break the chain of programmatic dependent launches (common.cuh)
+    if (c == 0) COVA_CUDA(cudaMemsetAsync(p->ccl.d_cursor, 0, 2 * sizeof(unsigned long long), p->stream));
     int rc = tensorise_chunk(p);
     if (!rc) rc = blobnet_chunk(p);
-    if (!rc) rc = ccl_range(p, p->ck_window0, (int)p->ck_windows, c == 0);
+    if (!rc) rc = ccl_range(p, p->ck_window0, (int)p->ck_windows, false);
     return rc;
 }
 
@@ -1209,6 +1213,7 @@ extern "C" int cova_pipeline_read_activation(cova_pipeline *p, int layer, float 
 extern "C" int cova_pipeline_set_debug(cova_pipeline *p, int flags) {
     if (!p) return set_err(COVA_E_INVAL, "null handle");
     p->dbg = flags;
+    g_pdl = !(flags & 32);      // bit 5: plain stream-ordered launches instead of programmatic dependent launch
     return COVA_OK;
 }
 extern "C" int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count) {

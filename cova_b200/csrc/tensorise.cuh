@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__res
 //     by pointwise_tn_kernel through the `newest` table.
 __global__ void __launch_bounds__(256) tensorise_frames_kernel(const uint32_t *__restrict__ frames, uint4 *__restrict__ x0f,
                                                                Geom g, int n_frames) {
+    pdl_launch_dependents();
+    pdl_wait();              // x0f is still being read by the previous batch's first block until that batch has completed
     const int Wh = g.Wh;
     const long long total = (long long)n_frames * g.H * Wh;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
