@@ -46,21 +46,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4 &a, const u
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// exact unsigned division by an invariant d >= 2 (Granlund-Montgomery, round-up variant)
-struct FastDiv { uint32_t m, s; };
-inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    uint32_t l = 0;
-    while ((1ull << l) < d) l++;
-    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    f.s = l - 1;
-    return f;
-}
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, FastDiv f) {
-    const uint32_t t = __umulhi(f.m, x);
-    return (t + ((x - t) >> 1)) >> f.s;
-}
-
 template <int CIN_CB_, int COUT_, int LA_, int LB_, int NP_, int TPS_, int EW_ = 16>
 struct ECfg {
     static constexpr int EW = EW_, CS = EW_ / 4;           // epilogue warps: CS per TMEM lane quarter, each owning a column range of a tile

@@ -30,7 +30,12 @@ struct CclArgs {
     int32_t *labels;          // optional [n][H][W]
     int32_t *stats;           // optional [n][(nb+1)*5]
     int32_t *n_labels;        // optional [n]
+    FastDiv div_nbx;          // block index -> (by, bx) of a thread's first block; later blocks advance by (step_by, step_bx)
+    int step_by, step_bx;     // blockDim.x / nbx, blockDim.x % nbx
 };
+
+// (by, bx) of block b + blockDim.x from those of block b
+#define COVA_CCL_ADVANCE(by, bx) do { bx += A.step_bx; by += A.step_by; if (bx >= A.nbx) { bx -= A.nbx; by++; } } while (0)
 
 __host__ __device__ inline size_t ccl_smem_bytes(int nb, int threads) {
     // parent + 5 stat arrays (int) + codes (u8, padded) + warp scan scratch
@@ -75,21 +80,33 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     //    neighbour" gives every block the first block of its run inside the warp's 32-block segment as parent
     //    (depth 1).  Without this a run of n blocks is a chain of n links that every later find walks.
     const int lane = tid & 31;
+    // no per-block division: (by, bx) of the thread's first block once, then incremental
+    const int by_first = A.nbx > 1 ? (int)fast_div((uint32_t)tid, A.div_nbx) : tid;
+    const int bx_first = tid - by_first * A.nbx;
+    const bool w_even = (A.W & 1) == 0;          // then every 2x2 block row is one aligned 16-bit load
+    int run_by = by_first, run_bx = bx_first;
     for (int base = 0; base < nb; base += nt) {
         const int b = base + tid;
-        int c = 0, bx = 0;
+        const int by = run_by, bx = run_bx;
+        COVA_CCL_ADVANCE(run_by, run_bx);
+        int c = 0;
         if (b < nb) {
-            const int by = b / A.nbx;
-            bx = b - by * A.nbx;
             const int y = 2 * by, x = 2 * bx;
             const uint8_t *r0 = m + (size_t)y * A.W + x;
-            const bool x1 = x + 1 < A.W, y1 = y + 1 < A.H;
+            const bool y1 = y + 1 < A.H;
             // plain (coherent) loads: under programmatic dependent launch the mask is written while this grid is
             // already resident, which rules out the read-only data path
-            c = (r0[0] != 0) ? 1 : 0;
-            if (x1 && r0[1] != 0) c |= 2;
-            if (y1 && r0[A.W] != 0) c |= 4;
-            if (x1 && y1 && r0[A.W + 1] != 0) c |= 8;
+            if (w_even) {
+                const unsigned v0 = *reinterpret_cast<const unsigned short *>(r0);
+                const unsigned v1 = y1 ? *reinterpret_cast<const unsigned short *>(r0 + A.W) : 0u;
+                c = ((v0 & 0xffu) ? 1 : 0) | ((v0 >> 8) ? 2 : 0) | ((v1 & 0xffu) ? 4 : 0) | ((v1 >> 8) ? 8 : 0);
+            } else {
+                const bool x1 = x + 1 < A.W;
+                c = (r0[0] != 0) ? 1 : 0;
+                if (x1 && r0[1] != 0) c |= 2;
+                if (y1 && r0[A.W] != 0) c |= 4;
+                if (x1 && y1 && r0[A.W + 1] != 0) c |= 8;
+            }
         }
         const int cw = __shfl_up_sync(0xffffffffu, c, 1);
         const bool west = lane > 0 && bx > 0 && (c & 0x5) && (cw & 0xA);       // my left column / its right column
@@ -98,17 +115,21 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             const int start_lane = 31 - __clz((int)(starts & (0xffffffffu >> (31 - lane))));
             code[b] = (uint8_t)c;
             parent[b] = c ? b - lane + start_lane : -1;
-            minx[b] = 0x7fffffff; miny[b] = 0x7fffffff; maxx[b] = -1; maxy[b] = -1; area[b] = 0;
+            if (c) {                                     // statistics live at roots, and only foreground blocks can be roots
+                minx[b] = 0x7fffffff; miny[b] = 0x7fffffff; maxx[b] = -1; maxy[b] = -1; area[b] = 0;
+            }
         }
     }
     __syncthreads();
 
     // 2. merge with the raster-preceding neighbour blocks: north, north-west, north-east, and west across a warp
     //    segment boundary (lane 0 could not see its west neighbour in step 1)
+    run_by = by_first; run_bx = bx_first;
     for (int b = tid; b < nb; b += nt) {
-        int c = code[b];
+        const int c = code[b];
+        const int by = run_by, bx = run_bx;
+        COVA_CCL_ADVANCE(run_by, run_bx);
         if (!c) continue;
-        int by = b / A.nbx, bx = b - by * A.nbx;
         if (lane == 0 && bx > 0 && (c & 0x5) && (code[b - 1] & 0xA)) uf_union(parent, b, b - 1);
         if (by > 0) {
             int u = b - A.nbx;
@@ -120,12 +141,14 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     __syncthreads();
 
     // 3. flatten + per-root statistics
+    run_by = by_first; run_bx = bx_first;
     for (int b = tid; b < nb; b += nt) {
-        int c = code[b];
+        const int c = code[b];
+        const int by = run_by, bx = run_bx;
+        COVA_CCL_ADVANCE(run_by, run_bx);
         if (!c) continue;
         int r = uf_find(parent, b);
         parent[b] = r;
-        int by = b / A.nbx, bx = b - by * A.nbx;
         int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
         int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
         atomicMin(&minx[r], x0); atomicMax(&maxx[r], x1);

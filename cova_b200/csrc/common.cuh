@@ -146,6 +146,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// exact unsigned division by an invariant d >= 2 (Granlund-Montgomery, round-up variant)
+struct FastDiv { uint32_t m, s; };
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) l++;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s = l - 1;
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, FastDiv f) {
+    const uint32_t t = __umulhi(f.m, x);
+    return (t + ((x - t) >> 1)) >> f.s;
+}
+
 struct alignas(16) Row8 {  // one 16-byte row: 8 fp16 channels
     __half v[8];
 };

@@ -223,6 +223,8 @@ static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_
     a.labels = want_labels ? b.d_labels : nullptr;
     a.stats = want_labels ? b.d_stats : nullptr;
     a.n_labels = want_labels ? b.d_nlabels : nullptr;
+    a.div_nbx = make_fastdiv((uint32_t)std::max(2, b.nbx));
+    a.step_by = b.threads / b.nbx; a.step_bx = b.threads % b.nbx;
     if (reset_cursor) COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
     COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, a));
     return COVA_OK;
