@@ -26,6 +26,7 @@ constexpr int MODE_ENC = 0, MODE_DEC = 1, MODE_HEAD = 2, MODE_ENCF = 3;   // ENC
 constexpr int kMaxStage = 4;
 constexpr int kEpiWarps = 16;                 // 4 groups of 4 warps (one per TMEM lane quarter)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kDecScratchRows = 68;            // decoder epilogue: 16-byte rows of transposition scratch per epilogue warp (epilogue_dec)
 constexpr int kScratchPitch = 36;              // floats per channel row of the quad-exchange scratch (32 lanes + 4: conflict-free 128-bit reads)
 
 struct LayerParams {
@@ -47,6 +48,7 @@ struct LayerParams {
     unsigned int *watchdog;            // set to a non-zero code if a barrier wait times out
     int bn_nonneg;                     // ENC: every BatchNorm scale of the layer is >= 0 (skips the min-pool path)
     int dbg;                           // experiments only: bit0 = skip the MMAs, bit1 = skip the epilogue math (results are garbage)
+    FastDiv divS, divP;                // exact division by gin.S and gin.P (epilogue position decode)
     int psplit;                        // DEC with 512 accumulator columns per tile: two half-tiles of two input phases each (see Cfg::CAN_SPLIT)
 };
 
@@ -124,6 +126,13 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, carrying a data dependence on the registers an EARLIER tcgen05.ld filled: in a double-buffered epilogue
+// the consumer of r[] is separated from its load by another load, and nothing else would keep the compiler from
+// scheduling the arithmetic on r[] above the wait.
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
 
 // shared-memory matrix descriptor, K-major, no swizzle, sm_100 version bit (cute SmemDescriptor)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -182,7 +191,7 @@ template <class C>
 __host__ __device__ constexpr int epi_floats() {
     // encoder: bias|scale|shift, two 4x4 TN matrices, then 256 floats of exchange scratch per epilogue warp
     return C::MODE == MODE_ENC ? 3 * C::COUT + 32 + kEpiWarps * 8 * kScratchPitch
-                               : (C::MODE == MODE_ENCF ? 3 * C::COUT : (C::MODE == MODE_DEC ? 2 * C::COUT : 4));
+                               : (C::MODE == MODE_ENCF ? 3 * C::COUT : (C::MODE == MODE_DEC ? 2 * C::COUT + kEpiWarps * kDecScratchRows * 4 : 4));
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issue
@@ -260,9 +269,9 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
     const Geom &gi = p.gin;
     const int t = pp & 3;
     const int qq = pp >> 2;
-    const int n = qq / gi.S;
+    const int n = (int)fast_div((uint32_t)qq, p.divS);
     const int r = qq - n * gi.S;
-    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const int y2 = (int)fast_div((uint32_t)r, p.divP), x2 = r - y2 * gi.P;
     const bool valid = n < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);   // same for the 4 lanes of a quad
     const int Y = y2 + (gi.H & 1), X = x2 + (gi.W & 1);          // zero-pad top / left when odd (encoder.py:68-76)
     const int pho = ((Y & 1) << 1) | (X & 1);
@@ -341,9 +350,9 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
 template <class C>
 __device__ __forceinline__ void epilogue_encf(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int cg) {
     const Geom &gi = p.gin;
-    const int f = pp / gi.S;
+    const int f = (int)fast_div((uint32_t)pp, p.divS);
     const int r = pp - f * gi.S;
-    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const int y2 = (int)fast_div((uint32_t)r, p.divP), x2 = r - y2 * gi.P;
     const bool valid = f < p.N && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);
     const int Y = y2 + (gi.H & 1), X = x2 + (gi.W & 1);          // zero-pad top / left when odd (encoder.py:68-76)
     long long row = 0;
@@ -381,48 +390,73 @@ __device__ __forceinline__ void epilogue_encf(const LayerParams &p, const float 
     }
 }
 
-// decoder: warp group `ph` owns the accumulator of input phase ph
+// Decoder tail.  Warp group g takes the input-row phase pa = g >> 1, BOTH column phases pb, and every second output parity
+// of the CTA (pl = g & 1, g & 1 + 2, ...).  Why both pb: output column X = 4*x2 + 2*pb + px - crop_l, so within one output
+// phase plane the rows of consecutive input positions x2 alternate between pb = 0 and pb = 1.  A warp that stores one pb
+// writes 16 bytes of every other 32-byte sector (measured: dec2 0.149 ms with that pattern, 0.100 ms with the same
+// stores coalesced); a warp that holds both writes whole sectors.  The rows go through a per-warp shared-memory scratch
+// (pb = 0 rows at [lane], pb = 1 rows at [36 + lane]: conflict-free both ways) so that lane L stores row L of a 32-row
+// run (positions 0..15 of the warp, then 16..31): each store instruction covers 512 contiguous bytes wherever the
+// positions of the warp are contiguous in the output plane.
 template <class C>
-__device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int half, int ph) {
+__device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *epi, uint4 *scratch, uint32_t taddr, int pp, int half,
+                                             int g, int lane) {
     const Geom &gi = p.gin;
-    const int n = pp / gi.S;
+    const int n = (int)fast_div((uint32_t)pp, p.divS);
     const int r = pp - n * gi.S;
-    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const int y2 = (int)fast_div((uint32_t)r, p.divP), x2 = r - y2 * gi.P;
     constexpr int PARN = C::NCOLS / C::COUT;   // output parities handled by this CTA
-    const float *scale = epi, *offs = epi + C::COUT;
-    const int oy = 2 * y2 + (ph >> 1), ox = 2 * x2 + (ph & 1);   // position in the (Hin+1) x (Win+1) sub-pixel grid
-    const bool vpos = n < p.N && oy <= gi.H && ox <= gi.W;
-    // dec0 (8 channel blocks per parity): the accumulator loads of one output parity are in flight together, one wait
-    // (0.105 -> 0.100 ms per 8192 windows at 720p).  dec1 / dec2 keep one load per wait: batching measured slower there
-    // (dec1 0.113 -> 0.121 per parity, -> 0.132 across parities; dec2 0.145 -> 0.153).
-    constexpr int CBN = C::COUT / 8, G = CBN >= 8 ? CBN : 1;
+    constexpr int CBN = C::COUT / 8;
+    static_assert(PARN % 2 == 0, "the two warp groups of a row phase split the parities");
+    const float4 *scale4 = reinterpret_cast<const float4 *>(epi), *offs4 = reinterpret_cast<const float4 *>(epi + C::COUT);
+    const int pa = g >> 1;
+    const int oy = 2 * y2 + pa, ox0 = 4 * x2;                      // sub-pixel grid position for pb = 0 is (oy, 2*x2); pb = 1 one to the right
+    const bool vrow = n < p.N && oy <= gi.H;
+    const int src_a = lane >> 1, src_b = 16 + (lane >> 1), my_pb = lane & 1;
+    const uint32_t acc0 = taddr + (uint32_t)((pa * 2) * C::NCOLS), acc1 = acc0 + (uint32_t)C::NCOLS;
 #pragma unroll 1
-    for (int pl = 0; pl < PARN; pl++) {
-        const int par = half * PARN + pl;
-        const int Y = 2 * oy + (par >> 1) - p.crop_t, X = 2 * ox + (par & 1) - p.crop_l;
-        const bool valid = vpos && Y >= 0 && Y < p.Ht && X >= 0 && X < p.Wt;
-        long long row = 0;
-        if (valid) row = geom_row(p.gout, 0, ((Y & 1) << 1) | (X & 1), geom_pos(p.gout, n, Y >> 1, X >> 1, 0));
+    for (int pl = g & 1; pl < PARN; pl += 2) {
+        const int par = half * PARN + pl, py = par >> 1, px = par & 1;
+        const int Y = 2 * oy + py - p.crop_t, X0 = ox0 + px - p.crop_l;             // pb = 1: X0 + 2, i.e. the next row of the same plane
+        const bool vy = vrow && Y >= 0 && Y < p.Ht;
+        const bool v0 = vy && X0 >= 0 && X0 < p.Wt && 2 * x2 <= gi.W;
+        const bool v1 = vy && X0 + 2 >= 0 && X0 + 2 < p.Wt && 2 * x2 + 1 <= gi.W;
+        const int plane = (((py - p.crop_t) & 1) << 1) | ((px - p.crop_l) & 1);     // warp-uniform
+        const int pos0 = (int)p.gout.guard + (n * p.gout.S + (Y >> 1) * p.gout.P + (X0 >> 1));   // arithmetic shifts: X0 may be -1
+        const unsigned m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
+        const unsigned mine = my_pb ? m1 : m0;
+        const bool va = (mine >> src_a) & 1u, vb = (mine >> src_b) & 1u;
+        const long long plane_row = (long long)plane * p.gout.Lp;
+        uint4 *dst_a = p.out + (plane_row + (__shfl_sync(0xffffffffu, pos0, src_a) + my_pb));
+        uint4 *dst_b = p.out + (plane_row + (__shfl_sync(0xffffffffu, pos0, src_b) + my_pb));
+        if (!(m0 | m1)) continue;                                                   // warp-uniform: nothing of this warp survives the crop
 #pragma unroll
-        for (int cb0 = 0; cb0 < CBN; cb0 += G) {
-            uint32_t v[G][8];
-#pragma unroll
-            for (int j = 0; j < G; j++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + pl * C::COUT + (cb0 + j) * 8), v[j]);
+        for (int cb = 0; cb < CBN; cb++) {
+            uint32_t a0[8], a1[8];
+            tmem_ld8(acc0 + (uint32_t)(pl * C::COUT + cb * 8), a0);
+            tmem_ld8(acc1 + (uint32_t)(pl * C::COUT + cb * 8), a1);
+            const float4 s0 = scale4[cb * 2], s1 = scale4[cb * 2 + 1], f0 = offs4[cb * 2], f1 = offs4[cb * 2 + 1];
             tmem_wait_ld();
-            if (valid) {
+            uint4 rw[2];
 #pragma unroll
-                for (int j = 0; j < G; j++) {
-                    const int cb = cb0 + j;
-                    float o[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        o[k] = fmaxf(fmaf(__uint_as_float(v[j][k]), scale[cb * 8 + k], offs[cb * 8 + k]), 0.f);   // bias+BN, then the consumer's ReLU
-                    uint4 rw;
-                    rw.x = pack_half2(o[0], o[1]); rw.y = pack_half2(o[2], o[3]);
-                    rw.z = pack_half2(o[4], o[5]); rw.w = pack_half2(o[6], o[7]);
-                    p.out[row + (long long)cb * 4 * p.gout.Lp] = rw;
-                }
+            for (int b = 0; b < 2; b++) {
+                const uint32_t(&a)[8] = b ? a1 : a0;
+                // bias+BN folded into (scale, offs), then the consumer's ReLU
+                const float2 o01 = relu2(ffma2(make_float2(__uint_as_float(a[0]), __uint_as_float(a[1])), make_float2(s0.x, s0.y), make_float2(f0.x, f0.y)));
+                const float2 o23 = relu2(ffma2(make_float2(__uint_as_float(a[2]), __uint_as_float(a[3])), make_float2(s0.z, s0.w), make_float2(f0.z, f0.w)));
+                const float2 o45 = relu2(ffma2(make_float2(__uint_as_float(a[4]), __uint_as_float(a[5])), make_float2(s1.x, s1.y), make_float2(f1.x, f1.y)));
+                const float2 o67 = relu2(ffma2(make_float2(__uint_as_float(a[6]), __uint_as_float(a[7])), make_float2(s1.z, s1.w), make_float2(f1.z, f1.w)));
+                rw[b].x = pack_half2(o01.x, o01.y); rw[b].y = pack_half2(o23.x, o23.y);
+                rw[b].z = pack_half2(o45.x, o45.y); rw[b].w = pack_half2(o67.x, o67.y);
             }
+            scratch[lane] = rw[0];
+            scratch[36 + lane] = rw[1];
+            __syncwarp();
+            const uint4 ra = scratch[my_pb * 36 + src_a], rb = scratch[my_pb * 36 + src_b];
+            __syncwarp();
+            const long long cb_row = (long long)cb * 4 * p.gout.Lp;
+            if (va) dst_a[cb_row] = ra;
+            if (vb) dst_b[cb_row] = rb;
         }
     }
 }
@@ -430,9 +464,9 @@ __device__ __forceinline__ void epilogue_dec(const LayerParams &p, const float *
 template <class C>
 __device__ __forceinline__ void epilogue_head(const LayerParams &p, const float *epi, uint32_t taddr, int pp, int ph) {
     const Geom &gi = p.gin;
-    const int n = pp / gi.S;
+    const int n = (int)fast_div((uint32_t)pp, p.divS);
     const int r = pp - n * gi.S;
-    const int y2 = r / gi.P, x2 = r - y2 * gi.P;
+    const int y2 = (int)fast_div((uint32_t)r, p.divP), x2 = r - y2 * gi.P;
     const float c0 = epi[0];
     uint32_t v[4];
     tmem_ld4(taddr + (uint32_t)(ph * C::NCOLS), v);
@@ -475,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
     pdl_launch_dependents();
 
     // epilogue constants -> smem (generic proxy)
-    constexpr int kEpiConst = C::MODE == MODE_ENC ? 3 * C::COUT + 32 : epi_floats<C>();
+    constexpr int kEpiConst = C::MODE == MODE_ENC ? 3 * C::COUT + 32 : (C::MODE == MODE_DEC ? 2 * C::COUT : epi_floats<C>());
     for (int i = threadIdx.x; i < kEpiConst; i += kThreads) {
         float v;
         if (C::MODE == MODE_ENC && i >= 3 * C::COUT) v = (i - 3 * C::COUT < 16) ? p.tn_w1[i - 3 * C::COUT] : p.tn_w2[i - 3 * C::COUT - 16];
@@ -599,7 +633,8 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                     if (p.dbg & 2) {
                     } else if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, scratch, taddr, pp, lane, cg);
                     else if constexpr (C::MODE == MODE_ENCF) epilogue_encf<C>(p, epi, taddr, pp, cg);
-                    else if constexpr (C::MODE == MODE_DEC) epilogue_dec<C>(p, epi, taddr, pp, half, cg);
+                    else if constexpr (C::MODE == MODE_DEC)
+                        epilogue_dec<C>(p, epi, reinterpret_cast<uint4 *>(epi + 2 * C::COUT) + (warp - 2) * kDecScratchRows, taddr, pp, half, cg, lane);
                     else epilogue_head<C>(p, epi, taddr, pp, cg);
                     tc_fence_before();
                     __syncwarp();
@@ -623,6 +658,8 @@ inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &e
     p.n_tiles = (int)((mtot + kTileM - 1) / kTileM);
     p.n_groups = (p.n_tiles + C::TPS - 1) / C::TPS;
     p.Ls = C::TPS * kTileM + 2 * p.gin.halo;
+    p.divS = make_fastdiv((uint32_t)p.gin.S);
+    p.divP = make_fastdiv((uint32_t)p.gin.P);
     if (4 * p.Ls >= 16384 || p.gin.P >= 16384) return false;                       // LBO field: 14 bits of 16-byte units
     if (p.gin.guard + (long long)p.n_groups * C::TPS * kTileM + p.gin.halo > p.gin.Lp) return false;
     const int nsplit = C::MODE == MODE_DEC ? p.nsplit : 1;
