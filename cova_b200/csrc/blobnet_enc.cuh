@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
                         if (u >= u_lo && u < u_hi && u < n_my && ((cur_vmask >> (4 * u)) & 15u)) {   // warp-uniform: skip padding units
                             const uint32_t orow = __shfl_sync(0xffffffffu, cur_o, 4 * u + pix_in_unit);
                             const uint32_t srow = __shfl_sync(0xffffffffu, cur_s, 4 * u + pix_in_unit);
-                            finalize_unit<C>(p, run_cur[u], ec, ecs, th, (cur_vmine & (1u << (4 * u))) != 0u && !(p.dbg & 128), outb, out2b, orow, srow, step_o, step_s);
+                            finalize_unit<C>(p, run_cur[u], ec, ecs, th, (cur_vmine & (1u << (4 * u))) != 0u, outb, out2b, orow, srow, step_o, step_s);
                         }
                 }
             }

@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""profiles/<tag>_ncu_summary.json (tools/ncu_summary.py) -> profiles/traffic.json: DRAM bytes per launch of every
+kernel of the path, keyed by the stage names bench.py reports.  usage: python tools/make_traffic.py r1e"""
+import json, os, re, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+rows = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.json")))
+RULES = [("tensorise_frames", r"tensorise_frames_kernel"), ("tc_enc1_fused", r"enc1_fused_kernel"),
+         ("tc_enc2", r"enc_ws_kernel<.*ECfg<2,"), ("tc_enc3", r"enc_ws_kernel<.*ECfg<4,|shiftgemm_kernel<.*Cfg<0, 4,"),
+         ("tc_enc4", r"enc_ws_kernel<.*ECfg<8,|shiftgemm_kernel<.*Cfg<0, 8,"),
+         ("tc_dec0", r"shiftgemm_kernel<.*Cfg<1, 16, 128, \d+, \d+, 64>"), ("tc_dec1", r"shiftgemm_kernel<.*Cfg<1, 16, 128, \d+, \d+, 32>"),
+         ("tc_dec2", r"shiftgemm_kernel<.*Cfg<1, 8,"), ("tc_dec3_head", r"shiftgemm_kernel<.*Cfg<2,"), ("ccl_bbox", r"ccl_bbox_kernel")]
+traffic, sass = {}, {}
+for r in rows:
+    for name, pat in RULES:
+        if re.search(pat, r["kernel"]) and "dram_bytes" in r:
+            traffic[name] = int(r["dram_bytes"]); sass[name] = r["kernel"]
+json.dump({"source": f"ncu --set full --clock-control none, tools/ncu_step.py (128 chains x 67 frames of 720p = 8192 windows, one chunk), "
+                     f"profiles/{tag}_ncu_summary.json", "windows_per_launch": 8192, "dram_bytes_per_launch": traffic, "sass_kernel": sass},
+          open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+print(traffic)
