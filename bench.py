@@ -206,7 +206,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from cova_b200 import _lib, synth
+    from cova_b200 import _lib, shard, synth
+    # several ranks on one box: each keeps its pinned frame / box buffers on its GPU's NUMA node (at N = 1 the CPU
+    # baseline leg wants every core, and there is no neighbour to share the inter-socket link with)
+    numa = shard.bind_rank_to_gpu(local_rank) if world > 1 else None
     from cova_b200.elements import BlobPipeline
 
     n_streams, fps = args.streams, FRAMES_PER_STREAM
@@ -337,7 +340,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "windows_per_gpu_per_step": n_windows, "timestep": T, "gamma": 1, "cc_threshold": 1,
                        "l2": "per-step working set (activations ~5 GB) far exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"chain-sharded x{world}, no collective", "weights": "random-init (seed 0), reference architecture"},
+                       "parallelism": f"chain-sharded x{world}, no collective", "weights": "random-init (seed 0), reference architecture",
+                       "host_numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.array.size), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roof, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -36,6 +36,7 @@ SIGNATURES = {
     "cova_last_error": (ctypes.c_char_p, []),
     "cova_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
     "cova_host_alloc": (ctypes.c_int, [_vpp, ctypes.c_size_t]),
+    "cova_bind_host_to_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "cova_host_free": (None, [_vp]),
     "cova_metapreprocess_new": (ctypes.c_int, [_vpp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "cova_metapreprocess_free": (None, [_vp]),

@@ -1,7 +1,9 @@
 // C ABI of libcova_b200.so (see include/cova_b200.h).  One translation unit: kernels + host plumbing.
 // There is NO CPU fallback anywhere in this file: without a CUDA device every constructor fails with
 // COVA_E_NODEVICE.
+#include <ctype.h>
 #include <math.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <mutex>
@@ -72,6 +74,52 @@ extern "C" int cova_host_alloc(void **out, size_t bytes) {
 }
 extern "C" void cova_host_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+// One process per GPU (DESIGN.md "Multi-GPU"): the frames of a rank travel host -> device at PCIe rate, so its pinned
+// buffers must live on the NUMA node the GPU hangs off - with 8 ranks on a two-socket box the inter-socket link is
+// otherwise shared by up to 4 x 55 GB/s of remote reads.  Restricting the calling thread to the GPU's local CPUs
+// (sysfs local_cpulist) before it allocates makes first-touch placement do that without libnuma.
+extern "C" int cova_bind_host_to_device(int device, int *numa_node, int *n_cpus) {
+    if (numa_node) *numa_node = -1;
+    if (n_cpus) *n_cpus = 0;
+    char bus[32] = "";
+    cudaError_t e = cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(COVA_E_NODEVICE, "cudaDeviceGetPCIBusId: %s", cudaGetErrorString(e)); }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    const std::string base = std::string("/sys/bus/pci/devices/") + bus;
+    if (FILE *f = fopen((base + "/numa_node").c_str(), "r")) {
+        int node = -1;
+        if (fscanf(f, "%d", &node) == 1 && numa_node) *numa_node = node;
+        fclose(f);
+    }
+    FILE *f = fopen((base + "/local_cpulist").c_str(), "r");
+    if (!f) return COVA_OK;                                   // no topology information: leave the affinity alone
+    char list[4096] = "";
+    const bool got = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!got) return COVA_OK;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int count = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); count++; }
+    }
+    if (!count) return COVA_OK;
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {        // stay inside what the launcher (cgroup, taskset) allows
+        cpu_set_t both;
+        CPU_AND(&both, &set, &cur);
+        if (CPU_COUNT(&both) == 0) return COVA_OK;
+        set = both;
+        count = CPU_COUNT(&both);
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return COVA_OK;
+    if (n_cpus) *n_cpus = count;
+    return COVA_OK;
 }
 extern "C" int cova_device_count(int *n) {
     if (!n) return set_err(COVA_E_INVAL, "null argument");

@@ -27,6 +27,18 @@ def gop_ranges(n_gops: int, n_pads: int) -> list[tuple[int, int]]:
     return out
 
 
+def bind_rank_to_gpu(device: int) -> dict:
+    """One process per GPU: keep this process (and the pinned frame/box buffers it allocates from now on) on the CPUs of
+    the NUMA node `device` hangs off (cova_bind_host_to_device).  Returns {"numa_node", "n_cpus"}; n_cpus == 0 means the
+    affinity was left alone (no topology information, or nothing left inside the launcher's own CPU set)."""
+    import ctypes
+
+    from . import _lib
+    node, ncpu = ctypes.c_int(-1), ctypes.c_int(0)
+    _lib.check(_lib.load().cova_bind_host_to_device(int(device), ctypes.byref(node), ctypes.byref(ncpu)))
+    return {"numa_node": node.value, "n_cpus": ncpu.value}
+
+
 def gop_starts(is_keyframe: list[bool]) -> list[int]:
     """Frame index at which every GoP starts (a buffer without DELTA_UNIT; gstgopsplit.cpp:712-723).  Delta
     frames ahead of the first key frame form a GoP of their own."""

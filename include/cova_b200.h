@@ -40,6 +40,11 @@ const char *cova_last_error(void);
 int cova_device_count(int *n);
 /* page-locked host memory: frame and box buffers in it let process_host overlap copies with kernels */
 int cova_host_alloc(void **out, size_t bytes);
+/* Multi-GPU, one process per GPU (the reference starts one pipeline process per `--cuda` device,
+ * experiment/cova/launch.py:33-93):
+ * restrict the calling thread to the CPUs local to `device` so that buffers it allocates afterwards are placed on the
+ * GPU's NUMA node.  numa_node / n_cpus (optional) report what was found; no topology information = no change. */
+int cova_bind_host_to_device(int device, int *numa_node, int *n_cpus);
 void cova_host_free(void *ptr);
 
 /* ------------------------------------------------------------------------------------------------

@@ -316,3 +316,18 @@ def test_async_submit_collect_batches_in_flight():
             p.submit(batches[k + 2])
         got.append(p.collect())
     assert got == want
+
+
+def test_bind_rank_to_gpu_keeps_the_process_inside_its_cpu_set():
+    """cova_bind_host_to_device: the affinity after the call is a non-empty subset of the one before (N>1 ranks of
+    bench.py call it before allocating their pinned buffers)."""
+    from cova_b200 import shard
+    before = os.sched_getaffinity(0)
+    try:
+        info = shard.bind_rank_to_gpu(0)
+        after = os.sched_getaffinity(0)
+        assert after and after <= before
+        assert info["n_cpus"] in (0, len(after))
+        assert info["numa_node"] >= -1
+    finally:
+        os.sched_setaffinity(0, before)

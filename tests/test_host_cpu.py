@@ -37,6 +37,9 @@ def test_no_cpu_fallback_without_device():
     rc = lib.cova_pipeline_new(ctypes.byref(h), 0, 80, 45, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1, 0)
     assert rc == _lib.E_NODEVICE
     assert b"no CPU fallback" in lib.cova_last_error()
+    node, ncpu = ctypes.c_int(7), ctypes.c_int(7)
+    assert lib.cova_bind_host_to_device(0, ctypes.byref(node), ctypes.byref(ncpu)) == _lib.E_NODEVICE
+    assert (node.value, ncpu.value) == (-1, 0)
 
 
 def test_argument_validation_comes_before_device_use():
