@@ -425,7 +425,7 @@ class BlobPipeline:
     def _worst_case_cap(self, n_windows: int) -> int:
         return n_windows * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
 
-    # ---- asynchronous streaming form: at most three batches in flight
+    # ---- asynchronous streaming form: at most four batches in flight
     def submit(self, frames: np.ndarray, blob_cap: int | None = None):
         """Enqueue one batch (copies + kernels) and return immediately.  `frames` should live in page-locked
         memory (PinnedBuffer) and must stay untouched until the matching collect()."""

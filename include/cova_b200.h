@@ -142,10 +142,11 @@ int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t
                                uint32_t frames_per_stream, uint8_t *blob, size_t blob_cap, size_t *blob_len,
                                uint64_t *offsets, uint64_t *lens, uint32_t *n_windows);
 
-/* Asynchronous form of process_host for steady-state streaming: at most three batches in flight.  submit returns
+/* Asynchronous form of process_host for steady-state streaming: at most four batches in flight.  submit returns
  * once the copies and kernels are enqueued (frames must stay valid, ideally page-locked, until the matching
  * collect); collect blocks for the oldest batch and copies its boxes out.  submit(k+1) before collect(k) hides
- * the host<->device copies of one batch behind the kernels of the other. */
+ * the host<->device copies of one batch behind the kernels of the other; submit(k+3) before collect(k) keeps the
+ * host->device copy engine busy back to back (the steady state is then bound by PCIe, not by a batch's latency). */
 int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t frames_per_stream);
 int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
                                uint64_t *lens, uint32_t *n_windows);

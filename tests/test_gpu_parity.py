@@ -305,17 +305,19 @@ def test_async_submit_collect_batches_in_flight():
     assert got == want
     with pytest.raises(_lib.CovaError):
         p.collect()                               # nothing in flight
-    p.submit(batches[0]); p.submit(batches[1]); p.submit(batches[2])
+    p.submit(batches[0]); p.submit(batches[1]); p.submit(batches[2]); p.submit(batches[3])
     with pytest.raises(_lib.CovaError):
-        p.submit(batches[3])                      # at most three in flight
-    assert [p.collect(), p.collect(), p.collect()] == want[:3]
-    got = []                                      # two ahead: submit k+2 before collect k
-    p.submit(batches[0]); p.submit(batches[1])
-    for k in range(len(batches)):
-        if k + 2 < len(batches):
-            p.submit(batches[k + 2])
-        got.append(p.collect())
-    assert got == want
+        p.submit(batches[4])                      # at most four in flight
+    assert [p.collect(), p.collect(), p.collect(), p.collect()] == want[:4]
+    for ahead in (2, 3):                          # submit k+ahead before collect k
+        got = []
+        for b in batches[:ahead]:
+            p.submit(b)
+        for k in range(len(batches)):
+            if k + ahead < len(batches):
+                p.submit(batches[k + ahead])
+            got.append(p.collect())
+        assert got == want
 
 
 def test_bind_rank_to_gpu_keeps_the_process_inside_its_cpu_set():

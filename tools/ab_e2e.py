@@ -12,7 +12,8 @@ n_streams, fps = 128, 67
 flags = [int(f) for f in os.environ.get("FLAGS", "0,32").split(",")]
 rounds, steps = int(os.environ.get("ROUNDS", 4)), int(os.environ.get("STEPS", 20))
 frames = synth.tiled_streams(n_streams, fps, 45, 80, 1)
-pins = [PinnedBuffer(frames.shape) for _ in range(3)]
+AHEAD = int(os.environ.get("AHEAD", 3))
+pins = [PinnedBuffer(frames.shape) for _ in range(AHEAD + 1)]
 for i, pb in enumerate(pins):
     pb.array[...] = np.roll(frames, i, axis=0)
 p = BlobPipeline(80, 45, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=int(os.environ.get("CHUNKS", 1)))
@@ -26,10 +27,11 @@ for r in range(rounds):
     for f in flags:
         p.set_debug(f)
         t0 = time.perf_counter()
-        p.submit(pins[0].array); p.submit(pins[1].array)
+        for k in range(AHEAD):
+            p.submit(pins[k].array)
         for k in range(steps):
-            if k + 2 < steps:
-                p.submit(pins[(k + 2) % 3].array)
+            if k + AHEAD < steps:
+                p.submit(pins[(k + AHEAD) % len(pins)].array)
             p.collect(raw=True)
         acc[f].append((time.perf_counter() - t0) * 1e3 / steps)
 for f in flags:
