@@ -273,6 +273,48 @@ def test_full_size_batch_properties():
     assert p.process(frames) == blobs
 
 
+def test_config_c3_1080p_shard_properties():
+    """BASELINE configs[2]: 1080p (120x68 macroblocks), 256 chains sharded by chain over 8 GPUs = 32 chains of 64 windows
+    per GPU.  Size-independent checks on one such shard: boxes bit-exact for the device mask (C oracle), duplicated chains
+    give identical windows, the stacked tensor of a sampled chain is bit-exact, a second run reproduces the first."""
+    from cova_b200 import shard
+    wts = weights.random_weights(0, head_bias=-1.0)
+    mine = shard.streams_of_rank(256, 8, 3)                           # the chains rank 3 of 8 owns
+    assert len(mine) == 32 and mine[0] == 3 and mine[1] == 11
+    frames = synth.tiled_streams(32, 67, 68, 120, config_idx=2, n_unique=4)
+    frames[16:] = frames[:16]
+    p = BlobPipeline(120, 68, weights.to_blob(wts), 32, 67, keep_stacked=True)
+    blobs = p.process(frames)
+    mask = p.read_mask()
+    assert len(blobs) == 32 * 64 and mask.shape == (32 * 64, 68, 120)
+    assert blobs == c_oracle.bboxcc_batch(mask, 1)
+    assert blobs[: 16 * 64] == blobs[16 * 64:]
+    assert (p.read_stacked()[5 * 64: 6 * 64] == mpr.tensorise_stream(frames[5], 4, 1)).all()
+    assert 0.005 < mask.mean() < 0.6
+    assert p.process(frames) == blobs
+
+
+@pytest.mark.parametrize("head_bias", [0.0, 0.6])
+def test_config_c4_4k_dense_worst_case(head_bias):
+    """BASELINE configs[3]: 4K (240x135 macroblocks), dense motion: a head bias at / above zero turns a third to most of
+    the random-weight mask into foreground, i.e. thousands of small components or a few with long label chains.  Boxes
+    bit-exact for the device mask, logits within the fp16 bar of the fp32 oracle on a sampled window."""
+    wts = weights.random_weights(1, head_bias=head_bias)
+    frames = synth.synth_streams(2, 12, 135, 240, config_idx=3)
+    p = BlobPipeline(240, 135, weights.to_blob(wts), 2, 12, keep_logits=True, keep_stacked=True)
+    blobs = p.process(frames)
+    mask, logits = p.read_mask(), p.read_logits()
+    assert len(blobs) == 2 * 9 and mask.mean() > 0.2
+    assert blobs == c_oracle.bboxcc_batch(mask, 1)
+    n_boxes = [len(deserialize_vec(b)) for b in blobs]
+    assert max(n_boxes) >= 1
+    stacked = p.read_stacked()[:2]
+    ref = blobnet_ref.blobnet_forward(wts, mpr.stacked_to_nchw(stacked, 4))
+    scale = float(np.abs(ref).max())
+    assert float(np.abs(logits[:2] - ref).max()) <= LOGIT_REL_TOL * scale
+    assert float(((logits[:2] > 0) != (ref > 0)).mean()) <= MAX_FLIP
+
+
 def test_chunked_overlapped_processing_matches_single_chunk():
     """process() splits a batch into chunks of whole chains and overlaps copies with kernels; the per-window
     results must not depend on the chunking (last chunk smaller than the others included)."""
