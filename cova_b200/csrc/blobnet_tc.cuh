@@ -160,7 +160,12 @@ struct Cfg {
     static constexpr int TMEM_COLS = pow2_cols(NSLOT * COLS_TILE);
     static constexpr int NTAP = MODE == MODE_ENC ? 9 : 4;
     static constexpr int KP = ENCF ? 1 : KCH / 2;                        // K=16 steps per tap inside a stage
-    static constexpr int BLOCKS = ENCF ? 6 : NTAP * (CIN_CB / 2);        // B blocks per N-half
+    // Encoder blocks with Cout <= 64: the two column phases of a pooling window that read the same input column are
+    // fed by ONE MMA of N = 2*Cout (weights_pack.cuh, pack_encoder): per row phase 3 x {N, 2N, 2N, N} MMAs per K step
+    // instead of 18 of N.  An MMA with the A operand in shared memory costs ~43 + N/2 cycles (section 3.1 of DESIGN.md),
+    // so halving the count of the N = 64 MMAs of block 3 saves a fifth of its tensor time.
+    static constexpr bool PAIR = MODE == MODE_ENC && NCOLS <= 64;
+    static constexpr int BLOCKS = ENCF ? 6 : (PAIR ? 18 * (CIN_CB / 2) : NTAP * (CIN_CB / 2));   // B blocks (of BLOCK_N rows) per N-half
     static constexpr int BLOCK_N = ENCF ? 4 * NCOLS : NCOLS;             // rows of one B block (= N of one MMA)
     // A decoder tile whose four phase accumulators fill all 512 TMEM columns (dec0, dec1) cannot be double-buffered as a
     // whole: its MMAs and its epilogue would alternate.  Such a tile is processed as two half-tiles (input phases 0,1 and
@@ -216,6 +221,33 @@ __device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_
             const int r0 = slot * Ls + row0 + fdiv2(u) * P + (st < 4 ? -1 : 1);
             const uint64_t adesc = make_desc(stage_addr + (uint32_t)r0 * 16u, st < 4 ? 16u : (uint32_t)P * 16u, 128u);
             umma_f16(d_tmem, adesc, bdesc0 + (uint64_t)(st * C::BLOCK_N * 2), idesc, st > 0 ? 1u : 0u);
+        }
+    } else if constexpr (C::PAIR) {
+        const uint32_t a_lbo = (uint32_t)(4 * Ls * 16);
+        constexpr uint32_t idesc2 = make_idesc(2 * C::NCOLS);
+        constexpr int voff[4] = {0, 1, 3, 5};
+#pragma unroll
+        for (int pa = 0; pa < 2; pa++) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int u = pa + dy;
+#pragma unroll
+                for (int ivi = 0; ivi < 4; ivi++) {
+                    const int iv = (ivi + 1) & 3, v = iv - 1;              // order v = 0, 1, 2, -1: the first MMA of a row phase covers both accumulators
+                    const bool two = iv == 1 || iv == 2;
+                    const int plane = ((u & 1) << 1) | (v & 1);
+                    const int r0 = plane * Ls + row0 + (fdiv2(u) * P + fdiv2(v)) * Tn;
+                    const uint32_t d = d_tmem + (uint32_t)((pa * 2 + (iv == 3 ? 1 : 0)) * C::NCOLS);
+#pragma unroll
+                    for (int kpl = 0; kpl < C::KP; kpl++) {
+                        const uint64_t adesc = make_desc(stage_addr + (uint32_t)((2 * kpl * 4) * Ls + r0) * 16u, a_lbo, 128u);
+                        const int kp = kc * C::KP + kpl;
+                        const uint32_t boff = (uint32_t)((((dy + 1) * (C::CIN_CB / 2) + kp) * 6 + voff[iv]) * C::NCOLS * 32);
+                        const uint64_t bdesc = make_desc(w_addr + boff, (uint32_t)(two ? 2 * C::NCOLS : C::NCOLS) * 16u, 128u);
+                        umma_f16(d, adesc, bdesc, two ? idesc2 : idesc, (kc > 0 || dy > -1 || ivi > 0 || kpl > 0) ? 1u : 0u);
+                    }
+                }
+            }
         }
     } else {
         const uint32_t a_lbo = (uint32_t)(4 * Ls * 16);

@@ -112,6 +112,26 @@ inline void pack_encoder(const HostWeights &hw, int i, PackedLayer &pl) {
                     }
                 }
             }
+    } else if (co_n <= 64) {
+        // "paired column phases" (blobnet_tc.cuh, Cfg::PAIR): per (dy, kpair) four operand blocks, one per input column
+        // offset v = -1..2 relative to the pooled pixel: v = -1 feeds only column phase b = 0 (tap dx = -1), v = 2 only
+        // b = 1 (dx = +1): N = Cout; v = 0 and v = 1 feed both phases with taps dx = v (b = 0) and dx = v - 1 (b = 1):
+        // N = 2*Cout, rows [phase 0 | phase 1] - one MMA instead of two.  Rows of a (dy, kpair) group: Cout * {1, 2, 2, 1}.
+        const int kp_n = ci_n / 16;
+        pl.blocks = 3 * kp_n * 6;                                  // in units of Cout rows
+        pl.b.assign((size_t)pl.blocks * co_n * 16, __float2half_rn(0.f));
+        const int voff[4] = {0, 1, 3, 5};                          // start of block v + 1 inside its group, in units of Cout rows
+        for (int dy = -1; dy <= 1; dy++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int iv = 0; iv < 4; iv++) {
+                    const int v = iv - 1, N = (iv == 1 || iv == 2) ? 2 * co_n : co_n;
+                    __half *blk = pl.b.data() + ((size_t)((dy + 1) * kp_n + kp) * 6 + voff[iv]) * co_n * 16;
+                    for (int n = 0; n < N; n++) {
+                        const int b = iv == 3 ? 1 : n / co_n, co = n % co_n, dx = v - b;   // single-phase blocks: b = 0 (v = -1) or 1 (v = 2)
+                        for (int k = 0; k < 16; k++)
+                            blk[((size_t)(k >> 3) * N + n) * 8 + (k & 7)] = __float2half_rn(W(co, kp * 16 + k, dy, dx));
+                    }
+                }
     } else {
         const int kp_n = ci_n / 16;
         pl.blocks = 9 * kp_n;
