@@ -27,7 +27,8 @@ constexpr int kMaxStage = 4;
 constexpr int kEpiWarps = 16;                 // 4 groups of 4 warps (one per TMEM lane quarter)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kDecScratchRows = 68;            // decoder epilogue: 16-byte rows of transposition scratch per epilogue warp (epilogue_dec)
-constexpr int kScratchPitch = 36;              // floats per channel row of the quad-exchange scratch (32 lanes + 4: conflict-free 128-bit reads)
+constexpr int kPairPitch = 72;                 // floats per channel-PAIR row of the quad-exchange scratch: 32 lanes x 2 channels + 8
+constexpr int kScratchPitch = kPairPitch / 2;  // per channel: the scratch of a warp is 8 channels x kScratchPitch floats
 
 struct LayerParams {
     const uint4 *in; Geom gin;
@@ -295,9 +296,40 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 //      channel) and each lane then computes TWO channels for ALL four output frames - no redundant 4x4
 //      products and no shuffles;
 //   3. each lane stores its 2-channel slice (4 bytes) of the four 16-byte output rows of the quad.
+// Part 1 (epilogue_enc_pool): drain this warp's accumulators, keeping only the pooled extremum per channel in registers -
+// the caller then hands the TMEM slot back to the MMA warp BEFORE part 2 (epilogue_enc) does the arithmetic and the stores,
+// so the MMAs of the tile after next never wait for a finalisation.
 template <class C>
-__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, float *scratch, uint32_t taddr, int pp,
-                                             int lane, int cg) {
+__device__ __forceinline__ void epilogue_enc_pool(const LayerParams &p, const float *epi, uint32_t taddr, int cg,
+                                                  float (&ext)[(C::COUT / 8) / C::CG][8]) {
+    constexpr int CB_PER = (C::COUT / 8) / C::CG;
+    const float *scale = epi + C::COUT;
+#pragma unroll
+    for (int i = 0; i < CB_PER; i++) {
+        const int cb = cg * CB_PER + i;
+        uint32_t v[4][8];
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            // MaxPool(BN(ReLU(x + b))): x -> fma(max(x + b, 0), s, sh) is monotone (non-decreasing for s >= 0,
+            // non-increasing for s < 0), so the pool maximum is attained at max(x) resp. min(x): bit-identical
+            // to pooling the four activated values, with a quarter of the arithmetic.
+            const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
+            const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
+            ext[i][j] = fmaxf(fmax3(a0, a1, a2), a3);
+            if (!p.bn_nonneg) {
+                const float lo = fminf(fminf(a0, a1), fminf(a2, a3));
+                ext[i][j] = scale[cb * 8 + j] >= 0.f ? ext[i][j] : lo;
+            }
+        }
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *epi, float *scratch, const float (&ext)[(C::COUT / 8) / C::CG][8],
+                                             int pp, int lane, int cg) {
     const Geom &gi = p.gin;
     const int t = pp & 3;
     const int qq = pp >> 2;
@@ -316,56 +348,43 @@ __device__ __forceinline__ void epilogue_enc(const LayerParams &p, const float *
                  *shift4 = reinterpret_cast<const float4 *>(epi + 2 * C::COUT);
     const int qbase = lane & ~3;
     constexpr int CB_PER = (C::COUT / 8) / C::CG;                 // channel blocks of this warp group
-#pragma unroll 1
-    for (int cb = cg * CB_PER; cb < (cg + 1) * CB_PER; cb++) {
-        uint32_t v[4][8];
+    // PointWiseTN matrices as packed broadcast pairs are taken straight from the kernel parameters (uniform registers)
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) tmem_ld8(taddr + (uint32_t)(ph * C::NCOLS + cb * 8), v[ph]);
+    for (int i = 0; i < CB_PER; i++) {
+        const int cb = cg * CB_PER + i;
         float bs[8], sc[8], sh[8];
         *reinterpret_cast<float4 *>(bs) = bias4[cb * 2]; *reinterpret_cast<float4 *>(bs + 4) = bias4[cb * 2 + 1];
         *reinterpret_cast<float4 *>(sc) = scale4[cb * 2]; *reinterpret_cast<float4 *>(sc + 4) = scale4[cb * 2 + 1];
         *reinterpret_cast<float4 *>(sh) = shift4[cb * 2]; *reinterpret_cast<float4 *>(sh + 4) = shift4[cb * 2 + 1];
-        tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            // MaxPool(BN(ReLU(x + b))): x -> fma(max(x + b, 0), s, sh) is monotone (non-decreasing for s >= 0,
-            // non-increasing for s < 0), so the pool maximum is attained at max(x) resp. min(x): bit-identical
-            // to pooling the four activated values, with a quarter of the arithmetic.
-            const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
-            const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
-            float ext = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-            if (!p.bn_nonneg) {
-                const float lo = fminf(fminf(a0, a1), fminf(a2, a3));
-                ext = sc[j] >= 0.f ? ext : lo;
-            }
-            scratch[j * kScratchPitch + lane] = fmaf(fmaxf(ext + bs[j], 0.f), sc[j], sh[j]);
+        for (int jp = 0; jp < 4; jp++) {
+            // bias -> ReLU -> BatchNorm on the pooled extremum, channel pairs in packed fp32 lanes
+            const float2 act = relu2(fadd2(make_float2(ext[i][2 * jp], ext[i][2 * jp + 1]), make_float2(bs[2 * jp], bs[2 * jp + 1])));
+            *reinterpret_cast<float2 *>(scratch + jp * kPairPitch + 2 * lane) =
+                ffma2(act, make_float2(sc[2 * jp], sc[2 * jp + 1]), make_float2(sh[2 * jp], sh[2 * jp + 1]));
         }
         __syncwarp();
-        // PointWiseTN (pointwise.py:18-26) for channels 2t, 2t+1 of this quad's position, all four output frames
-        uint32_t packed[4];
-        float y[2][4];
+        // PointWiseTN (pointwise.py:18-26) for the channel pair t of this quad's position, all four output frames:
+        // x[ti] = (channel 2t, channel 2t+1) of frame ti
+        const float4 xa = *reinterpret_cast<const float4 *>(scratch + t * kPairPitch + 2 * qbase);
+        const float4 xb = *reinterpret_cast<const float4 *>(scratch + t * kPairPitch + 2 * qbase + 4);
+        const float2 x[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+        float2 h1[4];
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-            const float4 x4 = *reinterpret_cast<const float4 *>(scratch + (2 * t + c) * kScratchPitch + qbase);
-            const float x[4] = {x4.x, x4.y, x4.z, x4.w};
-            float h1[4];
+        for (int m = 0; m < 4; m++) {
+            float2 h = fmul2(x[0], bc2(p.tn_w1[m]));
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                float h = 0.f;
-#pragma unroll
-                for (int ti = 0; ti < 4; ti++) h = fmaf(x[ti], p.tn_w1[ti * 4 + m], h);
-                h1[m] = fmaxf(h, 0.f);
-            }
-#pragma unroll
-            for (int to = 0; to < 4; to++) {
-                float h = 0.f;
-#pragma unroll
-                for (int m = 0; m < 4; m++) h = fmaf(h1[m], p.tn_w2[m * 4 + to], h);
-                y[c][to] = fmaxf(x[to] + fmaxf(h, 0.f), 0.f);
-            }
+            for (int ti = 1; ti < 4; ti++) h = ffma2(x[ti], bc2(p.tn_w1[ti * 4 + m]), h);
+            h1[m] = relu2(h);
         }
+        uint32_t packed[4];
 #pragma unroll
-        for (int to = 0; to < 4; to++) packed[to] = pack_half2(y[0][to], y[1][to]);
+        for (int to = 0; to < 4; to++) {                              // relu(x + relu(h2)) = max(x + h2, x, 0)
+            float2 h = x[to];
+#pragma unroll
+            for (int m = 0; m < 4; m++) h = ffma2(h1[m], bc2(p.tn_w2[m * 4 + to]), h);
+            packed[to] = pack_half2(fmax3(h.x, x[to].x, 0.f), fmax3(h.y, x[to].y, 0.f));
+        }
         if (valid) {
             if (p.out) {
                 uint32_t *d = dst1 + (long long)cb * 4 * p.gout.Lp * 4;   // rows are 4 x u32
@@ -662,8 +681,18 @@ __global__ void __launch_bounds__(kThreads, 1) shiftgemm_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col;
                     const int pp = tile * kTileM + q * 32 + lane;
+                    if constexpr (C::MODE == MODE_ENC) {
+                        float ext[(C::COUT / 8) / C::CG][8];
+                        if (!(p.dbg & 2)) epilogue_enc_pool<C>(p, epi, taddr, cg, ext);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(slot));          // accumulators are in registers: release the slot early
+                        if (!(p.dbg & 2)) epilogue_enc<C>(p, epi, scratch, ext, pp, lane, cg);
+                        tile_it++;
+                        continue;
+                    }
                     if (p.dbg & 2) {
-                    } else if constexpr (C::MODE == MODE_ENC) epilogue_enc<C>(p, epi, scratch, taddr, pp, lane, cg);
+                    }
                     else if constexpr (C::MODE == MODE_ENCF) epilogue_encf<C>(p, epi, taddr, pp, cg);
                     else if constexpr (C::MODE == MODE_DEC)
                         epilogue_dec<C>(p, epi, reinterpret_cast<uint4 *>(epi + 2 * C::COUT) + (warp - 2) * kDecScratchRows, taddr, pp, half, cg, lane);
