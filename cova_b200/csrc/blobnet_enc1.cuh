@@ -16,6 +16,8 @@
 // Warp roles as in blobnet_tc.cuh: warp 0 producer, warp 1 TMEM owner + MMA issuer, 16 epilogue warps
 // (TMEM lane quarter x channel block x tile of the pair).
 #pragma once
+#include <type_traits>
+
 #include "blobnet_tc.cuh"
 
 namespace cova {
@@ -167,8 +169,17 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
             const int pho = ((Y & 1) << 1) | (X & 1);
             const long long base_o = (long long)(cg * 4 + pho) * p.gout.Lp + p.gout.guard + ((long long)(Y >> 1) * p.gout.P + (X >> 1)) * kT;
             const long long base_s = (long long)((p.out2_cb + cg) * 4 + pho) * p.gout2.Lp + p.gout2.guard + (long long)(Y >> 1) * p.gout2.P + (X >> 1);
-            uint32_t r1[4] = {0, 0, 0, 0}, r2[4] = {0, 0, 0, 0}, r3[4] = {0, 0, 0, 0};   // frames i-1, i-2, i-3 (8 channels, fp16 pairs)
-            for (int i = w.start; i < w.i1; i++, it++) {
+            // Ring of the last four pooled frames: ring[s][k] = channel pair (2k, 2k+1) of the frame whose index is s mod 4,
+            // as fp32 values already rounded to fp16 (what the two-kernel path stores and re-reads).  The frame loop is
+            // unrolled four times over the ring phase R, so "frame i - t" is the compile-time slot (R - t) & 3: no
+            // rotation moves, and one fp16 round trip per frame instead of one conversion per frame and window.
+            float2 ring[4][4];
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) ring[sl][k] = make_float2(0.f, 0.f);
+            auto step = [&](auto R_, int i) {
+                constexpr int R = decltype(R_)::value;
                 const int slot = (int)(it % (uint32_t)kSlots1);
                 tc::mbar_wait(tfull0 + 8u * slot, (it / (uint32_t)kSlots1) & 1u, p.watchdog, 5u);
                 tc::tc_fence_after();
@@ -180,28 +191,31 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(tempty0 + 8u * slot);       // accumulators are in registers: release the slot early
-                if ((p.dbg & 2) || !warp_live) continue;
-                uint32_t cur[4];
+                it++;
+                if ((p.dbg & 2) || !warp_live) return;
                 {
-                    float bs[8], sc[8], sh[8], o[8];
+                    float bs[8], sc[8], sh[8], ext[8];
                     *reinterpret_cast<float4 *>(bs) = c4[cg * 2]; *reinterpret_cast<float4 *>(bs + 4) = c4[cg * 2 + 1];
                     *reinterpret_cast<float4 *>(sc) = c4[4 + cg * 2]; *reinterpret_cast<float4 *>(sc + 4) = c4[4 + cg * 2 + 1];
                     *reinterpret_cast<float4 *>(sh) = c4[8 + cg * 2]; *reinterpret_cast<float4 *>(sh + 4) = c4[8 + cg * 2 + 1];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         // MaxPool(BN(ReLU(x + b))) = BN(ReLU(max x + b)) for a non-negative BN scale, of min x otherwise
-                        // (see tc::epilogue_enc): one activation per channel instead of four
+                        // (see tc::epilogue_enc_pool): one activation per channel instead of four
                         const float a0 = __uint_as_float(v[0][j]), a1 = __uint_as_float(v[1][j]);
                         const float a2 = __uint_as_float(v[2][j]), a3 = __uint_as_float(v[3][j]);
-                        float ext = fmaxf(fmax3(a0, a1, a2), a3);
+                        ext[j] = fmaxf(fmax3(a0, a1, a2), a3);
                         if (!p.bn_nonneg) {
                             const float lo = fminf(fminf(a0, a1), fminf(a2, a3));
-                            ext = sc[j] >= 0.f ? ext : lo;
+                            ext[j] = sc[j] >= 0.f ? ext[j] : lo;
                         }
-                        o[j] = fmaf(fmaxf(ext + bs[j], 0.f), sc[j], sh[j]);
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) cur[k] = tc::pack_half2(o[2 * k], o[2 * k + 1]);
+                    for (int k = 0; k < 4; k++) {                        // bias -> ReLU -> BatchNorm on channel pairs (packed fp32)
+                        const float2 o = ffma2(relu2(fadd2(make_float2(ext[2 * k], ext[2 * k + 1]), make_float2(bs[2 * k], bs[2 * k + 1]))),
+                                               make_float2(sc[2 * k], sc[2 * k + 1]), make_float2(sh[2 * k], sh[2 * k + 1]));
+                        ring[R][k] = __half22float2(__floats2half2_rn(o.x, o.y));   // the pooled activation is an fp16 tensor
+                    }
                 }
                 const int rel = i - ex.first;
                 const bool emit = i >= w.i0 && rel >= 0 && (ex.gamma == 1 || rel % ex.gamma == 0);   // warp-uniform
@@ -210,11 +224,7 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
                     uint32_t o32[4][4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {                        // channel pair (2k, 2k+1) in the two packed fp32 lanes
-                        float2 x[4];
-                        x[0] = __half22float2(*reinterpret_cast<const __half2 *>(&cur[k]));
-                        x[1] = __half22float2(*reinterpret_cast<const __half2 *>(&r1[k]));
-                        x[2] = __half22float2(*reinterpret_cast<const __half2 *>(&r2[k]));
-                        x[3] = __half22float2(*reinterpret_cast<const __half2 *>(&r3[k]));
+                        const float2 x[4] = {ring[R][k], ring[(R + 3) & 3][k], ring[(R + 2) & 3][k], ring[(R + 1) & 3][k]};   // frames i, i-1, i-2, i-3
                         float2 h1[4];
 #pragma unroll
                         for (int m = 0; m < 4; m++) {                    // h1[m] = relu(sum_t x[t] W1[t][m])  (pointwise.py:18-21)
@@ -237,8 +247,12 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
                     stg256(dst + 2, make_uint4(o32[2][0], o32[2][1], o32[2][2], o32[2][3]), make_uint4(o32[3][0], o32[3][1], o32[3][2], o32[3][3]));
                     p.out2[base_s + n * (long long)p.gout2.S] = t0;
                 }
-#pragma unroll
-                for (int k = 0; k < 4; k++) { r3[k] = r2[k]; r2[k] = r1[k]; r1[k] = cur[k]; }
+            };
+            for (int i = w.start; i < w.i1;) {
+                step(std::integral_constant<int, 0>{}, i); if (++i >= w.i1) break;
+                step(std::integral_constant<int, 1>{}, i); if (++i >= w.i1) break;
+                step(std::integral_constant<int, 2>{}, i); if (++i >= w.i1) break;
+                step(std::integral_constant<int, 3>{}, i); ++i;
             }
         }
     }
