@@ -166,7 +166,10 @@ struct Cfg {
     // instead of 18 of N.  An MMA with the A operand in shared memory costs ~43 + N/2 cycles (section 3.1 of DESIGN.md),
     // so halving the count of the N = 64 MMAs of block 3 saves a fifth of its tensor time.
     static constexpr bool PAIR = MODE == MODE_ENC && NCOLS <= 64;
-    static constexpr int BLOCKS = ENCF ? 6 : (PAIR ? 18 * (CIN_CB / 2) : NTAP * (CIN_CB / 2));   // B blocks (of BLOCK_N rows) per N-half
+    // Transposed convs whose doubled weights still fit shared memory (dec2, head) pair their column phases the same way:
+    // 3 MMAs {2N, N, N} per (row phase, row tap, K step) instead of 4 of N (weights_pack.cuh, pack_decoder).
+    static constexpr bool PAIRD = (MODE == MODE_DEC || MODE == MODE_HEAD) && NCOLS * CIN_CB <= 512;
+    static constexpr int BLOCKS = ENCF ? 6 : (PAIR ? 18 * (CIN_CB / 2) : (PAIRD ? 2 : 1) * NTAP * (CIN_CB / 2));   // B blocks (of BLOCK_N rows) per N-half
     static constexpr int BLOCK_N = ENCF ? 4 * NCOLS : NCOLS;             // rows of one B block (= N of one MMA)
     // A decoder tile whose four phase accumulators fill all 512 TMEM columns (dec0, dec1) cannot be double-buffered as a
     // whole: its MMAs and its epilogue would alternate.  Such a tile is processed as two half-tiles (input phases 0,1 and
@@ -246,6 +249,33 @@ __device__ __forceinline__ void issue_tile(const LayerParams &p, uint32_t stage_
                         const uint32_t boff = (uint32_t)((((dy + 1) * (C::CIN_CB / 2) + kp) * 6 + voff[iv]) * C::NCOLS * 32);
                         const uint64_t bdesc = make_desc(w_addr + boff, (uint32_t)(two ? 2 * C::NCOLS : C::NCOLS) * 16u, 128u);
                         umma_f16(d, adesc, bdesc, two ? idesc2 : idesc, (kc > 0 || dy > -1 || ivi > 0 || kpl > 0) ? 1u : 0u);
+                    }
+                }
+            }
+        }
+    } else if constexpr (C::PAIRD) {
+        // transposed conv, column phases paired (weights_pack.cuh, pack_decoder): per row phase pa and row tap a, the input
+        // column offsets w = 0 (both column phases, N = 2*NCOLS), w = -1 (pb = 0) and w = +1 (pb = 1)
+        static_assert(PH0 % 2 == 0 && NPH % 2 == 0, "half-tiles are row phases");
+        const uint32_t a_lbo = (uint32_t)(4 * Ls * 16);
+        constexpr uint32_t idesc2 = make_idesc(2 * C::NCOLS);
+#pragma unroll
+        for (int pa = PH0 / 2; pa < (PH0 + NPH) / 2; pa++) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+#pragma unroll
+                for (int wi = 0; wi < 3; wi++) {
+                    const int w = wi == 0 ? 0 : (wi == 1 ? -1 : 1);        // paired block first: it initialises both accumulators
+                    const int plane = (((pa - a) & 1) << 1) | (w & 1);
+                    const int r0 = plane * Ls + row0 + (fdiv2(pa - a) * P + fdiv2(w)) * Tn;
+                    const uint32_t d = d_tmem + (uint32_t)((pa * 2 + (wi == 2 ? 1 : 0)) * C::NCOLS);
+#pragma unroll
+                    for (int kpl = 0; kpl < C::KP; kpl++) {
+                        const uint64_t adesc = make_desc(stage_addr + (uint32_t)((2 * kpl * 4) * Ls + r0) * 16u, a_lbo, 128u);
+                        const int kp = kc * C::KP + kpl;
+                        const uint32_t boff = (uint32_t)(((a * (C::CIN_CB / 2) + kp) * 4 + (wi == 0 ? 0 : wi + 1)) * C::NCOLS * 32);
+                        const uint64_t bdesc = make_desc(w_addr + boff, (uint32_t)(wi == 0 ? 2 * C::NCOLS : C::NCOLS) * 16u, 128u);
+                        umma_f16(d, adesc, bdesc, wi == 0 ? idesc2 : idesc, (kc > 0 || a > 0 || wi > 0 || kpl > 0) ? 1u : 0u);
                     }
                 }
             }

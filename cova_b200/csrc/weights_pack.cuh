@@ -191,14 +191,22 @@ inline void pack_encoder_ws(const HostWeights &hw, int i, int LA, int LB, Packed
             }
 }
 
-// Decoder layer i (< 3), N-half `half` of `nsplit`: N = (4/nsplit) parities x Cout; blocks [tap][kpair];
-// epi = scale|offset (per Cout).  Layer 3 (+ head): N = 16 (4 parities used); epi[0] = constant term.
+// Decoder layer i (< 3), N-half `half` of `nsplit`: N = (4/nsplit) parities x Cout; epi = scale|offset (per Cout).
+// Layer 3 (+ head): N = 16 (4 parities used); epi[0] = constant term.
+// Blocks are grouped per (row tap a, kpair) by the input COLUMN offset w = pb - b they read (pb = column phase of the
+// sub-pixel position, b = column tap), "paired column phases" as in pack_encoder: [w = 0: 2N rows = tap (a,0) for pb = 0 |
+// tap (a,1) for pb = 1] [w = -1: N rows, tap (a,1), pb = 0] [w = +1: N rows, tap (a,0), pb = 1] - the same 4N rows as four
+// separate taps TWICE (every tap serves both column phases), but three MMAs instead of four per (row phase, a, K step).
+// Used where the doubled weights still fit shared memory: dec2 and the head (blobnet_tc.cuh, Cfg::PAIRD); dec0 / dec1
+// keep one block per tap, [tap][kpair].
+inline size_t dec_block_half(int N, int a, int kp_n, int kp, int unit) { return ((size_t)(a * kp_n + kp) * 4 + unit) * N * 16; }
 inline void pack_decoder(const HostWeights &hw, int i, int nsplit, int half, PackedLayer &pl) {
     const int ci_n = kDecCin[i], co_n = kDecCout[i], kp_n = ci_n / 16;
     const auto &d = hw.dec[i];
     auto W = [&](int ci, int co, int ky, int kx) { return d.convt_w[((size_t)(ci * co_n + co) * 4 + ky) * 4 + kx]; };
-    pl.blocks = 4 * kp_n;
-    if (i < 3) {
+    const bool paired = i >= 2;
+    pl.blocks = (paired ? 8 : 4) * kp_n;
+    if (i < 2) {
         const int par_n = 4 / nsplit;
         pl.n_cols = par_n * co_n;
         pl.b.assign((size_t)pl.blocks * pl.n_cols * 16, __float2half_rn(0.f));
@@ -210,28 +218,53 @@ inline void pack_decoder(const HostWeights &hw, int i, int nsplit, int half, Pac
                         for (int k = 0; k < 16; k++)
                             put_b(pl.b, tp * kp_n + kp, pl.n_cols, pl_i * co_n + co, k, W(kp * 16 + k, co, py + 2 * a, px + 2 * b));
                 }
+    } else if (i < 3) {
+        const int par_n = 4 / nsplit;
+        pl.n_cols = par_n * co_n;
+        pl.b.assign((size_t)pl.blocks * pl.n_cols * 16, __float2half_rn(0.f));
+        const int N = pl.n_cols;
+        for (int a = 0; a < 2; a++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int blk = 0; blk < 3; blk++) {                 // 0: w = 0 (paired, 2N rows), 1: w = -1, 2: w = +1
+                    const int NB = blk == 0 ? 2 * N : N;
+                    __half *dst = pl.b.data() + dec_block_half(N, a, kp_n, kp, blk == 0 ? 0 : blk + 1);
+                    for (int n = 0; n < NB; n++) {
+                        const int b = blk == 0 ? n / N : (blk == 1 ? 1 : 0), nn = n % N;
+                        const int pl_i = nn / co_n, co = nn % co_n, par = half * par_n + pl_i, py = par >> 1, px = par & 1;
+                        for (int k = 0; k < 16; k++)
+                            dst[((size_t)(k >> 3) * NB + n) * 8 + (k & 7)] = __float2half_rn(W(kp * 16 + k, co, py + 2 * a, px + 2 * b));
+                    }
+                }
+    } else {
+        pl.n_cols = 16;
+        pl.b.assign((size_t)pl.blocks * 16 * 16, __float2half_rn(0.f));
+        for (int a = 0; a < 2; a++)
+            for (int kp = 0; kp < kp_n; kp++)
+                for (int blk = 0; blk < 3; blk++) {
+                    const int NB = blk == 0 ? 32 : 16;
+                    __half *dst = pl.b.data() + dec_block_half(16, a, kp_n, kp, blk == 0 ? 0 : blk + 1);
+                    for (int n = 0; n < NB; n++) {
+                        const int b = blk == 0 ? n / 16 : (blk == 1 ? 1 : 0), par = n % 16;
+                        if (par >= 4) continue;                      // N = 16 is the smallest MMA; 4 parities are used
+                        const int py = par >> 1, px = par & 1;
+                        for (int k = 0; k < 16; k++) {
+                            double acc = 0;
+                            for (int co = 0; co < co_n; co++) acc += (double)W(kp * 16 + k, co, py + 2 * a, px + 2 * b) * hw.head_w[co];
+                            dst[((size_t)(k >> 3) * NB + n) * 8 + (k & 7)] = __float2half_rn((float)acc);
+                        }
+                    }
+                }
+        double c0 = hw.head_b[0];
+        for (int co = 0; co < co_n; co++) c0 += (double)hw.head_w[co] * d.convt_b[co];
+        pl.epi.assign(4, (float)c0);
+    }
+    if (i < 3) {
         pl.epi.resize(2 * co_n);
         for (int co = 0; co < co_n; co++) {
             float s = d.gamma[co] / sqrtf(d.var[co] + kBnEps);
             pl.epi[co] = s;
             pl.epi[co_n + co] = (d.convt_b[co] - d.mean[co]) * s + d.beta[co];
         }
-    } else {
-        pl.n_cols = 16;
-        pl.b.assign((size_t)pl.blocks * 16 * 16, __float2half_rn(0.f));
-        for (int tp = 0; tp < 4; tp++)
-            for (int kp = 0; kp < kp_n; kp++)
-                for (int par = 0; par < 4; par++) {
-                    int py = par >> 1, px = par & 1, a = tp >> 1, b = tp & 1;
-                    for (int k = 0; k < 16; k++) {
-                        double acc = 0;
-                        for (int co = 0; co < co_n; co++) acc += (double)W(kp * 16 + k, co, py + 2 * a, px + 2 * b) * hw.head_w[co];
-                        put_b(pl.b, tp * kp_n + kp, 16, par, k, (float)acc);
-                    }
-                }
-        double c0 = hw.head_b[0];
-        for (int co = 0; co < co_n; co++) c0 += (double)hw.head_w[co] * d.convt_b[co];
-        pl.epi.assign(4, (float)c0);
     }
 }
 
