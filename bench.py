@@ -63,6 +63,26 @@ def layer_flops(h, w):
     return dict(zip(LAYERS, out)), tn1
 
 
+def layer_bytes(h, w):
+    """ALGORITHMIC HBM bytes per window of every BlobNet layer: each fp16 activation tensor read once and written once
+    (encoder: input [Cin,T,H,W], output [Cout,T,H',W'] unless it is the last block, t = 0 skip row [Cout,H',W'];
+    decoder: concatenated input, output; head: u8 mask).  Weights (<= 150 KB per layer) are not counted."""
+    enc_ch = [(3, 16), (16, 32), (32, 64), (64, 128)]
+    dec_ch = [(128, 64), (128, 32), (64, 16), (32, 16)]
+    out, sizes = {}, []
+    hh, ww = h, w
+    for i, (ci, co) in enumerate(enc_ch):
+        b_in = ci * T * hh * ww * 2
+        hh, ww = (hh + 1) // 2, (ww + 1) // 2
+        sizes.append((hh, ww))
+        out[LAYERS[i]] = b_in + (co * T * hh * ww * 2 if i < 3 else 0) + co * hh * ww * 2
+    for i, (ci, co) in enumerate(dec_ch):
+        b_in = ci * hh * ww * 2
+        hh, ww = sizes[2 - i] if i < 3 else (h, w)
+        out[LAYERS[4 + i]] = b_in + (co * hh * ww * 2 if i < 3 else h * w)
+    return out
+
+
 def kernel_work(h, w, n_boxes):
     """ALGORITHMIC work per window of every kernel: FLOPs for the tensor-bound ones, bytes for the HBM-bound ones
     (DESIGN.md section 3)."""
@@ -306,6 +326,7 @@ def main():
         pk = peaks()
         nbox = float(((lens.astype(np.int64) - 8) // 24).mean())
         work, fl = kernel_work(H_MB, W_MB, nbox)
+        lbytes = layer_bytes(H_MB, W_MB)
         traffic = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -321,6 +342,11 @@ def main():
             st = {"ms": round(ms, 4), "bound": bound, "layer": layer, "traffic": traffic.get(name)}
             if bound == "tensor":
                 st.update(achieved=round(per_s / 1e12, 1), unit="TFLOP/s", peak=pk["tflops"], frac=round(per_s / 1e12 / pk["tflops"], 4))
+                # the same launch against the OTHER roof: algorithmic activation bytes at the measured copy bandwidth.  Where
+                # hbm_frac > frac the layer's floor is its HBM time (enc2, dec2), the contraction notwithstanding.
+                gbs = lbytes[layer] * n_windows / (ms * 1e-3) / 1e9
+                st.update(hbm_achieved=round(gbs, 1), hbm_frac=round(gbs / pk["hbm_gbs"], 4),
+                          binding="hbm" if gbs / pk["hbm_gbs"] > st["frac"] else "tensor")
             else:
                 st.update(achieved=round(per_s / 1e9, 1), unit="GB/s", peak=pk["hbm_gbs"], frac=round(per_s / 1e9 / pk["hbm_gbs"], 4))
             stages[name] = st

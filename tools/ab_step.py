@@ -12,7 +12,7 @@ n_streams, fps = int(os.environ.get("STREAMS", 128)), 67
 h, w = int(os.environ.get("H", 45)), int(os.environ.get("W", 80))
 flags = [int(f) for f in os.environ.get("FLAGS", "0,32,64,96").split(",")]
 rounds = int(os.environ.get("ROUNDS", 8))
-p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=1)
+p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=int(os.environ.get("CHUNKS", 1)))
 p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
 for _ in range(5):
     p.run()
