@@ -240,6 +240,30 @@ def test_pipeline_is_deterministic_and_reusable():
     assert p.launch_count() == 3 * 10        # tensorise, fused block 1, 7 layer kernels, CCL
 
 
+def test_back_to_back_steps_under_programmatic_dependent_launch():
+    """Every kernel of a step is launched with programmatic stream serialization and waits (griddepcontrol.wait) only
+    after its prologue; buffers are re-used from step to step.  40 steps enqueued back to back (no host sync between
+    them) on a batch large enough for persistent grids must leave exactly the boxes and the mask of a single,
+    synchronised step - with and without the attribute, and with the batch split into chunks."""
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.tiled_streams(24, 19, 45, 80, config_idx=6, n_unique=6)
+    ref = None
+    for n_chunks, dbg in ((1, 32), (1, 0), (3, 0)):
+        p = BlobPipeline(80, 45, weights.to_blob(wts), 24, 19, n_chunks=n_chunks)
+        p.set_debug(dbg)
+        p.load_frames(frames)
+        p.run(); p.sync()
+        boxes, mask = p.fetch_boxes(), p.read_mask()
+        if ref is None:
+            ref = (boxes, mask)
+        assert boxes == ref[0] and (mask == ref[1]).all()
+        for _ in range(40):
+            p.run()
+        p.sync()
+        assert p.fetch_boxes() == ref[0] and (p.read_mask() == ref[1]).all()
+        p.set_debug(0)
+
+
 def test_byte3_and_values_above_six_do_not_matter():
     """byte 3 is stale decoder garbage and BlobNet clips at 6 (preprocessing.py:5-8)."""
     wts = weights.random_weights(2, head_bias=-1.0)
