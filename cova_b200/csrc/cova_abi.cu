@@ -714,8 +714,10 @@ static int tensorise_chunk(cova_pipeline *p) {
         const int F = (int)(p->ck_n_streams * p->cur_fps);
         long long total = (long long)F * p->H * p->gx0f.Wh;
         int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
+        if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the frame tensorisation kernel (32-bit index)");
         COVA_CUDA(launch_pdl(tensorise_frames_kernel, dim3((unsigned)blocks), dim3(256), 0, p->stream,
-                             reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F));
+                             reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F,
+                             make_fastdiv((uint32_t)std::max(2, p->gx0f.Wh)), make_fastdiv((uint32_t)std::max<uint32_t>(2u, p->H))));
         p->launches++;
         prof_mark(p, "tensorise_frames");
     }

@@ -75,30 +75,54 @@ __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__res
 //     Tn = 1 phase-plane geometry whose "windows" are the frames of the pool.  The first convolution runs once
 //     per frame on this; the window structure (newest-first stacking of `timestep` frames) is applied afterwards
 //     by pointwise_tn_kernel through the `newest` table.
+// fp16 of the clipped bytes without integer->float conversions: 0x6400 | n is the half 1024 + n for n < 1024, and
+// subtracting 1024 in half arithmetic is exact.  q = [mb_weight, |mv_x|, |mv_y|, stale]; returns (c0 c1 | c2 0) as two half2.
+__device__ __forceinline__ uint2 quad_to_half4(uint32_t q) {
+    const uint32_t m = __vminu4(q, 0x06060606u);                       // clip(., 0, 6) of a u8 = min(., 6), all four bytes at once
+    const uint32_t lo = __byte_perm(m, 0u, 0x4140) | 0x64006400u;      // bytes 0, 1 into the low byte of each half
+    const uint32_t hi = __byte_perm(m, 0u, 0x4442) | 0x64006400u;      // byte 2; the fourth channel stays 0 (byte 3 is dropped)
+    const __half2 k = __half2half2(__ushort_as_half((unsigned short)0x6400));
+    const __half2 a = __hsub2(*reinterpret_cast<const __half2 *>(&lo), k), b = __hsub2(*reinterpret_cast<const __half2 *>(&hi), k);
+    return make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+}
+
 __global__ void __launch_bounds__(256) tensorise_frames_kernel(const uint32_t *__restrict__ frames, uint4 *__restrict__ x0f,
-                                                               Geom g, int n_frames) {
+                                                               Geom g, int n_frames, FastDiv div_wh, FastDiv div_h) {
     pdl_launch_dependents();
     pdl_wait();              // x0f is still being read by the previous batch's first block until that batch has completed
-    const int Wh = g.Wh;
-    const long long total = (long long)n_frames * g.H * Wh;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        int x2 = (int)(i % Wh);
-        long long r = i / Wh;
-        int y = (int)(r % g.H);
-        int f = (int)(r / g.H);
-        const uint32_t *src = frames + ((long long)f * g.H + y) * g.W + 2 * x2;
-        uint32_t q0 = __ldg(src);
-        uint32_t q1 = (2 * x2 + 1 < g.W) ? __ldg(src + 1) : 0u;
-        __half2 a01 = __floats2half2_rn((float)min(q0 & 0xffu, 6u), (float)min((q0 >> 8) & 0xffu, 6u));
-        __half2 a2z = __floats2half2_rn((float)min((q0 >> 16) & 0xffu, 6u), 0.f);
-        __half2 b01 = __floats2half2_rn((float)min(q1 & 0xffu, 6u), (float)min((q1 >> 8) & 0xffu, 6u));
-        __half2 b2z = __floats2half2_rn((float)min((q1 >> 16) & 0xffu, 6u), 0.f);
-        uint4 row;
-        row.x = *reinterpret_cast<uint32_t *>(&a01); row.y = *reinterpret_cast<uint32_t *>(&a2z);
-        row.z = *reinterpret_cast<uint32_t *>(&b01); row.w = *reinterpret_cast<uint32_t *>(&b2z);
-        x0f[geom_row(g, 0, (y & 1) << 1, geom_pos(g, f, y >> 1, x2, 0))] = row;
+    const uint32_t Wh = (uint32_t)g.Wh, H = (uint32_t)g.H, W = (uint32_t)g.W;
+    const uint32_t total = (uint32_t)n_frames * H * Wh;                 // host guarantees < 2^32
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const bool pair_aligned = (W & 1u) == 0u;                          // then an x pair is one aligned 8-byte load
+    // four x pairs per thread and iteration, loads first: a thread keeps 4 x 8 bytes in flight (with one load per
+    // iteration a full SM has 16 KB outstanding, half of what the HBM latency-bandwidth product asks for)
+    constexpr int U = 4;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        uint32_t q0[U], q1[U], rr[U], xx[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            const uint32_t i = i0 + (uint32_t)k * stride;
+            q0[k] = q1[k] = 0u; rr[k] = xx[k] = 0u;
+            if (i < total) {
+                const uint32_t r = Wh > 1 ? fast_div(i, div_wh) : i, x2 = i - r * Wh;      // r = f * H + y
+                const uint32_t *src = frames + ((size_t)r * W + 2 * x2);
+                rr[k] = r; xx[k] = x2;
+                if (pair_aligned) {
+                    const uint2 q = __ldg(reinterpret_cast<const uint2 *>(src));
+                    q0[k] = q.x; q1[k] = q.y;
+                } else {
+                    q0[k] = __ldg(src);
+                    q1[k] = (2 * x2 + 1 < W) ? __ldg(src + 1) : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; k++) {
+            if (i0 + (uint32_t)k * stride >= total) break;
+            const uint32_t f = H > 1 ? fast_div(rr[k], div_h) : rr[k], y = rr[k] - f * H;
+            const uint2 a = quad_to_half4(q0[k]), b = quad_to_half4(q1[k]);
+            x0f[geom_row(g, 0, (int)((y & 1u) << 1), geom_pos(g, (int)f, (int)(y >> 1), (int)xx[k], 0))] = make_uint4(a.x, a.y, b.x, b.y);
+        }
     }
 }
 
