@@ -180,9 +180,14 @@ def time_cpu(w, steps, warmup, target_s=5.0):
     for _ in range(steps):
         n += cpu_path(frames, w, threads)
     dt = time.perf_counter() - t0
+    # one core: the reference runs every chain single-threaded (SURVEY.md section 8d asks for both figures)
+    t1 = time.perf_counter()
+    n_one = cpu_path(probe, w, 1)
+    dt_one = time.perf_counter() - t1
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_streams} chains x {fps} frames of 720p per step ({n // steps} windows), {steps} steps, "
-                      f"C oracle tensorise/CCL + torch-CPU fp32 BlobNet, {threads} threads"}, dt / steps * 1e3, n1
+                      f"C oracle tensorise/CCL + torch-CPU fp32 BlobNet, {threads} threads",
+            "one_core": {"value": n_one / dt_one, "unit": UNIT, "cores": 1, "sample": f"2 chains x {fps} frames ({n_one} windows), 1 thread"}}, dt / steps * 1e3, n1
 
 
 # ------------------------------------------------------------------------------------------------ main
