@@ -64,8 +64,10 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     extern __shared__ __align__(16) unsigned char ccl_smem[];
     const int nb = A.nbx * A.nby;
     int *parent = reinterpret_cast<int *>(ccl_smem);
-    int *minx = parent + nb, *miny = minx + nb, *maxx = miny + nb, *maxy = maxx + nb, *area = maxy + nb;
-    uint8_t *code = reinterpret_cast<uint8_t *>(area + nb);
+    // per-block statistics interleaved, [block][min x, min y, max x, max y, area]: one base address per block (stride of 5
+    // words = conflict-free across a warp) instead of five array bases
+    int *stat = parent + nb;
+    uint8_t *code = reinterpret_cast<uint8_t *>(stat + 5 * nb);
     int *scan = reinterpret_cast<int *>(code + ((nb + 15) / 16) * 16);
     __shared__ unsigned long long s_off;
 
@@ -92,7 +94,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         int c = 0;
         if (b < nb) {
             const int y = 2 * by, x = 2 * bx;
-            const uint8_t *r0 = m + (size_t)y * A.W + x;
+            const uint8_t *r0 = m + (unsigned)(y * A.W + x);           // one mask is far below 2^31 pixels: 32-bit offset
             const bool y1 = y + 1 < A.H;
             // plain (coherent) loads: under programmatic dependent launch the mask is written while this grid is
             // already resident, which rules out the read-only data path
@@ -116,7 +118,8 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             code[b] = (uint8_t)c;
             parent[b] = c ? b - lane + start_lane : -1;
             if (c) {                                     // statistics live at roots, and only foreground blocks can be roots
-                minx[b] = 0x7fffffff; miny[b] = 0x7fffffff; maxx[b] = -1; maxy[b] = -1; area[b] = 0;
+                int *sb = stat + 5 * b;
+                sb[0] = 0x7fffffff; sb[1] = 0x7fffffff; sb[2] = -1; sb[3] = -1; sb[4] = 0;
             }
         }
     }
@@ -151,9 +154,10 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         parent[b] = r;
         int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
         int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
-        atomicMin(&minx[r], x0); atomicMax(&maxx[r], x1);
-        atomicMin(&miny[r], y0); atomicMax(&maxy[r], y1);
-        atomicAdd(&area[r], __popc(c));
+        int *sr = stat + 5 * r;
+        atomicMin(&sr[0], x0); atomicMax(&sr[2], x1);
+        atomicMin(&sr[1], y0); atomicMax(&sr[3], y1);
+        atomicAdd(&sr[4], __popc(c));
     }
     __syncthreads();
 
@@ -162,7 +166,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     const int b0 = min(tid * ipt, nb), b1 = min(b0 + ipt, nb);
     int cnt = 0;
     for (int b = b0; b < b1; b++)
-        if (parent[b] == b) cnt += 0x10000 + (area[b] >= A.area_thresh ? 1 : 0);
+        if (parent[b] == b) cnt += 0x10000 + (stat[5 * b + 4] >= A.area_thresh ? 1 : 0);
     int incl = cnt;
     const int wid = tid >> 5;
 #pragma unroll
@@ -209,7 +213,8 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     int rank_all = excl >> 16, rank_keep = excl & 0xffff;
     for (int b = b0; b < b1; b++) {
         if (parent[b] != b) continue;
-        int x0 = minx[b], y0 = miny[b], w = maxx[b] - x0 + 1, h = maxy[b] - y0 + 1, ar = area[b];
+        int *sb = stat + 5 * b;
+        int x0 = sb[0], y0 = sb[1], w = sb[2] - x0 + 1, h = sb[3] - y0 + 1, ar = sb[4];
         rank_all++;
         if (st) {
             int32_t *s5 = st + (size_t)rank_all * 5;
@@ -228,7 +233,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             }
             rank_keep++;
         }
-        area[b] = rank_all;
+        sb[4] = rank_all;                    // the area slot becomes the root -> label map
     }
     if (!A.labels) return;
     __syncthreads();
@@ -236,7 +241,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     for (int p = tid; p < A.H * A.W; p += nt) {
         int y = p / A.W, x = p - y * A.W;
         int b = (y >> 1) * A.nbx + (x >> 1);
-        lab[p] = (m[p] != 0) ? area[parent[b]] : 0;
+        lab[p] = (m[p] != 0) ? stat[5 * parent[b] + 4] : 0;
     }
 }
 
