@@ -143,7 +143,11 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     }
     __syncthreads();
 
-    // 3. flatten + per-root statistics
+    // 3. flatten + per-root statistics.  parent[b] = root is written while other threads may still walk through b in
+    //    their own uf_find: they read either b's old parent (an ancestor) or its root, and reach the same root either
+    //    way (aligned 32-bit accesses; no link is ever removed in this phase).  compute-sanitizer --tool racecheck reports
+    //    exactly this read/write pair and nothing else in the library; separating the two would cost a second pass or
+    //    another nb words of shared memory, which the 4K grid (196 KB already) does not have.
     run_by = by_first; run_bx = bx_first;
     for (int b = tid; b < nb; b += nt) {
         const int c = code[b];
