@@ -143,11 +143,10 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     }
     __syncthreads();
 
-    // 3. flatten + per-root statistics.  parent[b] = root is written while other threads may still walk through b in
-    //    their own uf_find: they read either b's old parent (an ancestor) or its root, and reach the same root either
-    //    way (aligned 32-bit accesses; no link is ever removed in this phase).  compute-sanitizer --tool racecheck reports
-    //    exactly this read/write pair and nothing else in the library; separating the two would cost a second pass or
-    //    another nb words of shared memory, which the 4K grid (196 KB already) does not have.
+    // 3. flatten + per-root statistics.  parent[b] is lowered to the root while other threads may still walk through b in
+    //    their own uf_find: they read either b's old parent (an ancestor) or its root and reach the same root either way.
+    //    The update is an atomicMin like the links of step 2 (the root is the smallest index on the path), which keeps
+    //    every concurrent access to parent[] an atomic or a volatile load (compute-sanitizer --tool racecheck: clean).
     run_by = by_first; run_bx = bx_first;
     for (int b = tid; b < nb; b += nt) {
         const int c = code[b];
@@ -155,7 +154,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         COVA_CCL_ADVANCE(run_by, run_bx);
         if (!c) continue;
         int r = uf_find(parent, b);
-        parent[b] = r;
+        atomicMin(&parent[b], r);
         int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
         int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
         int *sr = stat + 5 * r;
