@@ -35,8 +35,9 @@ constexpr int kPairRows = 2 * kTileM;
 struct Enc1Extra {
     int n_chains, fps, wps, gamma, first;   // chains of this chunk, frames per chain, windows per chain, sub-sampling, T - 1
     int ntp;                                // tile pairs per frame
-    int nseg, seg_len;                      // frame segments per chain
-    int n_items;                            // n_chains * ntp * nseg
+    int n_items;                            // (chain, tile pair) items = n_chains * ntp, each fps frame steps long
+    int full_items;                         // items handed out whole, round-robin: a multiple of the grid size
+    int total, span;                        // frame steps in all items / consecutive steps of the REMAINING items per CTA
 };
 
 struct SmemPlan1 {
@@ -56,15 +57,35 @@ __host__ __device__ inline SmemPlan1 plan_smem1(int Ls, int n_stage, int w_bytes
 struct Item {
     int chain, jp, i0, i1, start;
 };
-__device__ __forceinline__ Item decode_item(const Enc1Extra &ex, int item) {
-    Item it;
-    const int seg = item % ex.nseg, rest = item / ex.nseg;
-    it.jp = rest % ex.ntp;
-    it.chain = rest / ex.ntp;
-    it.i0 = seg * ex.seg_len;
-    it.i1 = min(ex.fps, it.i0 + ex.seg_len);
-    it.start = max(0, it.i0 - (kT - 1));
-    return it;
+// Work partition.  An item = one (chain, tile pair) walked through its fps frames; consecutive items are the tile pairs
+// of one chain, and handing them out round-robin keeps the CTAs that run concurrently on the same few chains (the four
+// tile pairs of a frame read and write neighbouring DRAM pages - a flat split of the whole step sequence into 148 spans
+// balanced better and ran 12 % slower).  Only the items left over after the last whole round (items mod grid size) are
+// cut: their steps form one sequence that is split evenly, and a CTA whose piece starts inside an item re-computes the
+// kT - 1 warm-up frames the register ring needs.  At the benchmark size: 3 whole items + a 31-step piece = 235 steps per
+// CTA for 232 of work (whole items only: 268; two fixed segments per item: 259).
+struct WorkIter {
+    int item, g, g1;
+};
+__device__ __forceinline__ WorkIter work_begin(const Enc1Extra &ex, int cta) {
+    WorkIter wi;
+    wi.item = cta;
+    wi.g = ex.full_items * ex.fps + cta * ex.span;
+    wi.g1 = min(ex.total, wi.g + ex.span);
+    return wi;
+}
+__device__ __forceinline__ bool work_next(const Enc1Extra &ex, int n_cta, WorkIter &wi, Item &it) {
+    if (wi.item < ex.full_items) {                                   // a whole item
+        it.jp = wi.item % ex.ntp; it.chain = wi.item / ex.ntp; it.i0 = 0; it.i1 = ex.fps; it.start = 0;
+        wi.item += n_cta;
+        return true;
+    }
+    if (wi.g >= wi.g1) return false;
+    const int item = wi.g / ex.fps, i = wi.g - item * ex.fps;          // a piece of a left-over item
+    const int len = min(ex.fps - i, wi.g1 - wi.g);
+    it.jp = item % ex.ntp; it.chain = item / ex.ntp; it.i0 = i; it.i1 = i + len; it.start = max(0, i - (kT - 1));
+    wi.g += len;
+    return true;
 }
 
 __device__ __forceinline__ void stg256(uint4 *dst, const uint4 &a, const uint4 &b) {
@@ -112,8 +133,8 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
         // ===== producer: the two row-parity strips of one frame per step =====
         if (tc::elect_one()) {
             uint32_t it = 0;
-            for (int item = cta; item < ex.n_items; item += n_cta) {
-                const Item w = decode_item(ex, item);
+            Item w;
+            for (WorkIter wi = work_begin(ex, cta); work_next(ex, n_cta, wi, w);) {
                 for (int i = w.start; i < w.i1; i++, it++) {
                     const int s = (int)(it % (uint32_t)p.n_stage);
                     tc::mbar_wait(empty0 + 8u * s, ((it / (uint32_t)p.n_stage) & 1u) ^ 1u, p.watchdog, 1u);
@@ -133,8 +154,8 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
             constexpr uint32_t idesc = tc::make_idesc(C1::BLOCK_N);
             tc::mbar_wait(w_bar, 0u, p.watchdog, 2u);
             uint32_t it = 0;
-            for (int item = cta; item < ex.n_items; item += n_cta) {
-                const Item w = decode_item(ex, item);
+            Item w;
+            for (WorkIter wi = work_begin(ex, cta); work_next(ex, n_cta, wi, w);) {
                 for (int i = w.start; i < w.i1; i++, it++) {
                     const int s = (int)(it % (uint32_t)p.n_stage);
                     tc::mbar_wait(full0 + 8u * s, (it / (uint32_t)p.n_stage) & 1u, p.watchdog, 3u);
@@ -159,8 +180,8 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
         const Geom &gi = p.gin;
         const float4 *c4 = reinterpret_cast<const float4 *>(epi);
         uint32_t it = 0;
-        for (int item = cta; item < ex.n_items; item += n_cta) {
-            const Item w = decode_item(ex, item);
+        Item w;
+        for (WorkIter wi = work_begin(ex, cta); work_next(ex, n_cta, wi, w);) {
             const int r = w.jp * kPairRows + tg * kTileM + q * 32 + lane;
             const int y2 = r / gi.P, x2 = r - y2 * gi.P;
             const bool valid = r < gi.S && y2 < (gi.H >> 1) && x2 < (gi.W >> 1);
@@ -261,20 +282,6 @@ __global__ void __launch_bounds__(kThreads1, 1) enc1_fused_kernel(const __grid_c
     if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// Segment count that minimises (rounds of items over the SMs) x (frames per item incl. 3 warm-up frames).
-inline void plan_segments(Enc1Extra &ex, int n_sms) {
-    long long best = -1;
-    for (int nseg = 1; nseg <= 16; nseg++) {
-        const int seg_len = (ex.fps + nseg - 1) / nseg;
-        if (nseg > 1 && seg_len < 2 * kT) break;
-        const int real = (ex.fps + seg_len - 1) / seg_len;
-        const long long items = (long long)ex.n_chains * ex.ntp * real;
-        const long long rounds = (items + n_sms - 1) / n_sms;
-        const long long cost = rounds * (seg_len + (real > 1 ? kT - 1 : 0));
-        if (best < 0 || cost < best) { best = cost; ex.nseg = real; ex.seg_len = seg_len; ex.n_items = (int)items; }
-    }
-}
-
 inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t st, cudaError_t &err) {
     p.Ls = kPairRows + 2 * p.gin.halo;
     if (p.gin.P >= 16384) return false;                                            // LBO field: 14 bits of 16-byte units
@@ -284,7 +291,12 @@ inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t
     if (p.gin.guard + (F - 1) * p.gin.S + (long long)ex.ntp * kPairRows + p.gin.halo > p.gin.Lp) return false;   // strip over-read stays inside the plane
     if ((p.gout.Lp & 1) || (p.gout.guard & 1)) return false;                       // 256-bit stores need 32-byte aligned rows
     p.w_bytes = C1::BLOCKS * C1::BLOCK_N * 32;
-    plan_segments(ex, n_sms);
+    if (F * ex.ntp >= (1ll << 31)) return false;
+    ex.total = (int)(F * ex.ntp);
+    ex.n_items = ex.n_chains * ex.ntp;
+    const int ctas = std::max(1, std::min(n_sms, ex.total));
+    ex.full_items = (ex.n_items / ctas) * ctas;
+    ex.span = ((ex.n_items - ex.full_items) * ex.fps + ctas - 1) / ctas;
     for (p.n_stage = kMaxStage1; p.n_stage >= 2; p.n_stage--)
         if (plan_smem1(p.Ls, p.n_stage, p.w_bytes).total <= (uint32_t)tc::kSmemLimit) break;
     if (p.n_stage < 2) return false;
@@ -292,7 +304,6 @@ inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t
     const uint32_t total = std::max<uint32_t>(plan_smem1(p.Ls, p.n_stage, p.w_bytes).total, 120u * 1024u);
     err = cudaFuncSetAttribute(enc1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
     if (err != cudaSuccess) return true;
-    const int ctas = std::max(1, std::min(n_sms, ex.n_items));
     err = launch_pdl(enc1_fused_kernel, dim3((unsigned)ctas), dim3(kThreads1), total, st, p, ex);
     return true;
 }
