@@ -88,7 +88,10 @@ def kernel_work(h, w, n_boxes):
     (DESIGN.md section 3)."""
     fl, tn1 = layer_flops(h, w)
     h1, w1 = (h + 1) // 2, (w + 1) // 2
-    work = {"tensorise_frames": 20 * h * w,                                   # each frame read once + RGBA stack written
+    fpw = FRAMES_PER_STREAM / (FRAMES_PER_STREAM - T + 1)                      # frames per window of a 67-frame chain
+    work = {# every frame read once (4 B per MB) + the per-FRAME fp16 input of the first conv written once (16 B per x pair);
+            # SURVEY 8d counts 20*W*H per window for a per-window RGBA stack, which this path never materialises
+            "tensorise_frames": fpw * (4 * h * w + 16 * h * ((w + 1) // 2)),
             # fused block 1: one packed input frame read + the window's 4 time planes + the t=0 skip copy written
             "tc_enc1_fused": 16 * h * ((w + 1) // 2) + 16 * h1 * w1 * 2 * (T + 1),
             "tc_enc1_conv": fl["enc1"] - tn1,
