@@ -7,11 +7,13 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libcova_b200.so")
+SO_VAL_PATH = os.path.join(_HERE, "libcova_b200_val.so")   # product sources + the validation kernels (tests only)
 
 OK, DROPPED = 0, 1
 E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE, E_NUMERIC, E_STATE = -1, -2, -3, -4, -5, -6, -7, -8, -9
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
 FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED = 0x100, 0x200
+SUBMIT_CONTINUE = 1
 
 
 class CovaError(RuntimeError):
@@ -66,6 +68,9 @@ SIGNATURES = {
     "cova_pipeline_process_host": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p]),
     "cova_pipeline_submit_host": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
     "cova_pipeline_collect_host": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p]),
+    "cova_pipeline_submit_host2": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_uint32]),
+    "cova_pipeline_collect_host2": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p, _vp, _vp]),
+    "cova_pipeline_reset_streams": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32]),
     "cova_pipeline_load_masks": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_int]),
     "cova_pipeline_read_stacked": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "cova_pipeline_read_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
@@ -124,25 +129,38 @@ SIGNATURES.update({
 })
 
 _lib = None
+_lib_val = None
+
+
+def _open(path: str) -> ctypes.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -m cova_b200.build` (nvcc, sm_100a). "
+                          "cova_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
 
 
 def load() -> ctypes.CDLL:
     """Load the shared library (built in-tree by cova_b200/build.py).  Raises if it is absent."""
     global _lib
     if _lib is None:
-        if not os.path.exists(SO_PATH):
-            raise ImportError(f"{SO_PATH} is missing: run `python -m cova_b200.build` (nvcc, sm_100a). "
-                              "cova_b200 has no CPU fallback.")
-        lib = ctypes.CDLL(SO_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
+        _lib = _open(SO_PATH)
     return _lib
 
 
-def check(rc: int) -> int:
+def load_validation() -> ctypes.CDLL:
+    """The validation build (product + COVA_IMPL_SIMT kernels): only the layer-by-layer parity tests ask for it."""
+    global _lib_val
+    if _lib_val is None:
+        _lib_val = _open(SO_VAL_PATH)
+    return _lib_val
+
+
+def check(rc: int, lib: ctypes.CDLL | None = None) -> int:
     if rc < 0:
-        raise CovaError(rc, load().cova_last_error().decode(errors="replace"))
+        raise CovaError(rc, (lib or load()).cova_last_error().decode(errors="replace"))
     return rc

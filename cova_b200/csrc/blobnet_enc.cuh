@@ -468,7 +468,7 @@ inline bool try_launch_e(LayerParams p, int n_sms, cudaStream_t st, cudaError_t 
     ex.divP = make_fastdiv((uint32_t)p.gin.P);
     int ctas = std::min(n_sms, p.n_groups);
     if (ctas < 1) ctas = 1;
-    err = launch_pdl(enc_ws_kernel<C>, dim3((unsigned)ctas), dim3(C::THREADS), sp.total, st, p, ex);
+    err = launch_pdl(enc_ws_kernel<C>, dim3((unsigned)ctas), dim3(C::THREADS), sp.total, st, !(p.dbg & kDbgNoPdl), p, ex);
     return true;
 }
 

@@ -304,7 +304,7 @@ inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t
     const uint32_t total = std::max<uint32_t>(plan_smem1(p.Ls, p.n_stage, p.w_bytes).total, 120u * 1024u);
     err = cudaFuncSetAttribute(enc1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
     if (err != cudaSuccess) return true;
-    err = launch_pdl(enc1_fused_kernel, dim3((unsigned)ctas), dim3(kThreads1), total, st, p, ex);
+    err = launch_pdl(enc1_fused_kernel, dim3((unsigned)ctas), dim3(kThreads1), total, st, !(p.dbg & kDbgNoPdl), p, ex);
     return true;
 }
 

@@ -766,7 +766,7 @@ inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &e
     int ctas = n_sms / nsplit;
     if (ctas > p.n_groups) ctas = p.n_groups;
     if (ctas < 1) ctas = 1;
-    err = launch_pdl(shiftgemm_kernel<C>, dim3((unsigned)(ctas * nsplit)), dim3(kThreads), sp.total, st, p);
+    err = launch_pdl(shiftgemm_kernel<C>, dim3((unsigned)(ctas * nsplit)), dim3(kThreads), sp.total, st, !(p.dbg & kDbgNoPdl), p);
     return true;
 }
 

@@ -8,7 +8,11 @@
 #include <algorithm>
 #include <mutex>
 
+// The fp32 CUDA-core validation kernels (COVA_IMPL_SIMT: layer-by-layer comparison partner of the tcgen05 kernels in the
+// tests) are only compiled into libcova_b200_val.so (-DCOVA_VALIDATION); the shipped library holds the hot path alone.
+#ifdef COVA_VALIDATION
 #include "blobnet_simt.cuh"
+#endif
 #include "blobnet_tc.cuh"
 #include "blobnet_enc.cuh"
 #include "blobnet_enc1.cuh"
@@ -19,7 +23,6 @@
 
 namespace cova {
 thread_local char g_err[512] = "";
-bool g_pdl = true;
 
 static int check_device(int device) {
     int n = 0;
@@ -248,7 +251,6 @@ static int ccl_alloc(CclBuffers &b, int H, int W, int max_masks, bool own_masks)
     COVA_CUDA(cudaMalloc(&b.d_cursor, 2 * sizeof(unsigned long long)));
     COVA_CUDA(cudaMalloc(&b.d_offsets, (size_t)max_masks * sizeof(unsigned long long)));
     COVA_CUDA(cudaMalloc(&b.d_lens, (size_t)max_masks * sizeof(unsigned long long)));
-    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
     return COVA_OK;
 }
 static void ccl_free(CclBuffers &b, bool own_masks) {
@@ -262,7 +264,7 @@ static void ccl_free(CclBuffers &b, bool own_masks) {
     if (b.d_nlabels) cudaFree(b.d_nlabels);
 }
 static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_threshold, bool want_labels, cudaStream_t st,
-                      size_t first = 0, bool reset_cursor = true) {
+                      size_t first = 0, bool reset_cursor = true, bool pdl = true) {
     if (n <= 0) return COVA_OK;
     CclArgs a;
     a.masks = d_masks + first * (size_t)b.H * b.W; a.H = b.H; a.W = b.W; a.nbx = b.nbx; a.nby = b.nby;
@@ -274,7 +276,10 @@ static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_
     a.div_nbx = make_fastdiv((uint32_t)std::max(2, b.nbx));
     a.step_by = b.threads / b.nbx; a.step_bx = b.threads % b.nbx;
     if (reset_cursor) COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
-    COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, a));
+    // the attribute is per function AND per device, last write wins: handles of different grids (or on different devices)
+    // share ccl_bbox_kernel, so it is set for every launch like the tcgen05 kernels do (try_launch)
+    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+    COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, pdl, a));
     return COVA_OK;
 }
 
@@ -383,7 +388,15 @@ struct cova_pipeline {
     size_t frame_bytes = 0;
     uint8_t *d_frames = nullptr;
     int *d_newest = nullptr;
-    uint32_t cur_streams = 0, cur_fps = 0, cur_windows = 0, table_streams = 0, table_fps = 0;
+    uint32_t cur_streams = 0, cur_fps = 0, cur_windows = 0, table_streams = 0, table_fps = 0, table_first = 0;
+    // index (inside a device chain) of the newest frame of the chain's first window, and windows per chain: T - 1 and
+    // (fps - T) / gamma + 1 for a chain that starts with an empty window; a CONTINUED chain (submit_host2) starts with the
+    // carried T - 1 frames of its stream and its first window sits where the stream's gamma phase puts it
+    uint32_t cur_first = 0, cur_wps = 0;
+    // per-stream state for CONTINUED batches (metapreprocess/imp.rs:38-42: prev_buffers and gamma_idx live as long as the
+    // stream): the last T - 1 frames of every stream id on the device, frames seen so far on the host
+    uint8_t *d_carry = nullptr;
+    std::vector<uint64_t> n_seen;
     // A batch is processed in chunks of whole chains: the activation buffers are sized for ONE chunk, and
     // process_host() overlaps the H2D copy of chunk c+1, the kernels of chunk c and the D2H of chunk c-1.
     uint32_t chunk_streams = 0;          // chains per chunk (capacity)
@@ -399,8 +412,11 @@ struct cova_pipeline {
         CclBuffers ccl;
         std::vector<cudaEvent_t> ev_in, ev_done;
         unsigned long long *h_cursor = nullptr;      // pinned: per-chunk cursor snapshots (2 words each)
-        uint32_t n_streams = 0, fps = 0, n_windows = 0;
-        bool busy = false;
+        uint32_t n_streams = 0, fps = 0, n_windows = 0, wps = 0;
+        bool busy = false, failed = false, ready = false;
+        uint32_t *h_ids = nullptr, *d_ids = nullptr;   // stream ids of a submit_host2 batch (pinned staging + device copy)
+        std::vector<uint64_t> win_pts;                 // per window: PTS of its newest frame / stream id (submit_host2)
+        std::vector<uint32_t> win_ids;
     } slot[kSlots];
     int cur_slot = 0, next_submit = 0, next_collect = 0;
     int sizes_h[5], sizes_w[5];          // extents: [0] input, [1..4] encoder outputs
@@ -433,6 +449,8 @@ static uint32_t windows_per_stream(uint32_t fps, uint32_t T, uint32_t gamma) {
     if (fps < T) return 0;
     return (fps - T) / gamma + 1;
 }
+// windows of a device chain of `fps` frames whose first window has its newest frame at index `first`
+static uint32_t windows_from(uint32_t fps, uint32_t first, uint32_t gamma) { return fps > first ? (fps - 1 - first) / gamma + 1 : 0; }
 
 static void prof_mark(cova_pipeline *p, const char *name) {
     if (!p->profiling) return;
@@ -471,6 +489,10 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     if (gamma < 1 || !max_streams || max_fps < timestep) return set_err(COVA_E_INVAL, "need gamma >= 1, max_streams >= 1, max_frames_per_stream >= timestep");
     if (w_mb < 16 || h_mb < 16) return set_err(COVA_E_UNSUPPORTED, "macroblock grid must be at least 16x16 for four 2x poolings");
     if ((flags & 0xffu) > COVA_IMPL_SIMT) return set_err(COVA_E_INVAL, "unknown implementation selector");
+#ifndef COVA_VALIDATION
+    if ((flags & 0xffu) == COVA_IMPL_SIMT)
+        return set_err(COVA_E_UNSUPPORTED, "the validation kernels (COVA_IMPL_SIMT) are not part of this build; use libcova_b200_val.so");
+#endif
     int rc = check_device(device);
     if (rc) return rc;
     auto *p = new (std::nothrow) cova_pipeline();
@@ -549,6 +571,7 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     if (e != cudaSuccess) return fail(set_err(COVA_E_CUDA, "pipeline allocation: %s", cudaGetErrorString(e)));
     p->slot[0].ccl.d_masks = p->d_mask;
     if ((rc = ccl_alloc(p->slot[0].ccl, (int)h_mb, (int)w_mb, std::max(1, NB), false))) return fail(rc);
+    p->slot[0].ready = true;
     p->ccl = p->slot[0].ccl;
     for (auto &sl : p->slot)
         if (cudaMallocHost(&sl.h_cursor, sizeof(unsigned long long) * 2 * 256) != cudaSuccess)
@@ -596,10 +619,13 @@ extern "C" void cova_pipeline_free(cova_pipeline *p) {
         if (sl.d_frames) cudaFree(sl.d_frames);
         ccl_free(sl.ccl, false);
         if (sl.h_cursor) cudaFreeHost(sl.h_cursor);
+        if (sl.h_ids) cudaFreeHost(sl.h_ids);
+        if (sl.d_ids) cudaFree(sl.d_ids);
         for (auto e : sl.ev_in) cudaEventDestroy(e);
         for (auto e : sl.ev_done) cudaEventDestroy(e);
     }
     if (p->d_newest) cudaFree(p->d_newest);
+    if (p->d_carry) cudaFree(p->d_carry);
     if (p->d_mask) cudaFree(p->d_mask);
     if (p->d_logits) cudaFree(p->d_logits);
     if (p->d_stacked) cudaFree(p->d_stacked);
@@ -630,23 +656,25 @@ extern "C" int cova_pipeline_n_windows(const cova_pipeline *p, uint32_t n_stream
     return COVA_OK;
 }
 
-static int set_batch_shape(cova_pipeline *p, uint32_t n_streams, uint32_t fps) {
+static int set_batch_shape(cova_pipeline *p, uint32_t n_streams, uint32_t fps, uint32_t first = 0xffffffffu) {
     if (!n_streams || n_streams > p->max_streams || fps > p->max_fps)
         return set_err(COVA_E_INVAL, "batch exceeds max_streams / max_frames_per_stream of the pipeline");
-    const uint32_t wps = windows_per_stream(fps, p->T, p->gamma);
-    if (n_streams * wps > p->max_windows) return set_err(COVA_E_INVAL, "batch produces more windows than the pipeline was sized for");
+    if (first == 0xffffffffu) first = p->T - 1;                   // chains that start with an empty window
+    const uint32_t wps = windows_from(fps, first, p->gamma);
+    if ((uint64_t)n_streams * wps > p->max_windows) return set_err(COVA_E_INVAL, "batch produces more windows than the pipeline was sized for");
     p->cur_streams = n_streams; p->cur_fps = fps; p->cur_windows = n_streams * wps;
+    p->cur_first = first; p->cur_wps = wps;
     const uint32_t tstreams = std::min(n_streams, p->chunk_streams);
-    if (p->table_streams != tstreams || p->table_fps != fps) {
+    if (p->table_streams != tstreams || p->table_fps != fps || p->table_first != first) {
         // chunk-relative table: window k of a chunk -> index (inside the chunk's frames) of its newest frame
         std::vector<int> &newest = p->h_newest;
         newest.assign(std::max<size_t>(1, (size_t)tstreams * wps), 0);
         size_t k = 0;
         for (uint32_t s = 0; s < tstreams; s++)
-            for (uint32_t w = 0; w < wps; w++) newest[k++] = (int)(s * fps + (p->T - 1) + w * p->gamma);
+            for (uint32_t w = 0; w < wps; w++) newest[k++] = (int)(s * fps + first + w * p->gamma);
         if (k) COVA_CUDA(cudaMemcpyAsync(p->d_newest, newest.data(), sizeof(int) * k, cudaMemcpyHostToDevice, p->stream));
         COVA_CUDA(cudaStreamSynchronize(p->stream));
-        p->table_streams = tstreams; p->table_fps = fps;
+        p->table_streams = tstreams; p->table_fps = fps; p->table_first = first;
     }
     return COVA_OK;
 }
@@ -654,7 +682,7 @@ static int set_batch_shape(cova_pipeline *p, uint32_t n_streams, uint32_t fps) {
 static void use_slot(cova_pipeline *p, int k);
 static uint32_t n_chunks_of(const cova_pipeline *p) { return (p->cur_streams + p->chunk_streams - 1) / p->chunk_streams; }
 static void select_chunk(cova_pipeline *p, uint32_t c) {
-    const uint32_t wps = windows_per_stream(p->cur_fps, p->T, p->gamma);
+    const uint32_t wps = p->cur_wps;
     p->ck_stream0 = c * p->chunk_streams;
     p->ck_n_streams = std::min(p->chunk_streams, p->cur_streams - p->ck_stream0);
     p->ck_window0 = p->ck_stream0 * wps;
@@ -715,12 +743,13 @@ static int tensorise_chunk(cova_pipeline *p) {
         long long total = (long long)F * p->H * p->gx0f.Wh;
         int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
         if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the frame tensorisation kernel (32-bit index)");
-        COVA_CUDA(launch_pdl(tensorise_frames_kernel, dim3((unsigned)blocks), dim3(256), 0, p->stream,
+        COVA_CUDA(launch_pdl(tensorise_frames_kernel, dim3((unsigned)blocks), dim3(256), 0, p->stream, !(p->dbg & kDbgNoPdl),
                              reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F,
                              make_fastdiv((uint32_t)std::max(2, p->gx0f.Wh)), make_fastdiv((uint32_t)std::max<uint32_t>(2u, p->H))));
         p->launches++;
         prof_mark(p, "tensorise_frames");
     }
+#ifdef COVA_VALIDATION
     if (p->x[0]) {   // window-layout input of the validation kernels
         long long total = (long long)N * p->H * p->gx[0].Wh * kT;
         int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
@@ -729,6 +758,7 @@ static int tensorise_chunk(cova_pipeline *p) {
         p->launches++;
         prof_mark(p, "tensorise_x0");
     }
+#endif
     return COVA_OK;
 }
 
@@ -746,6 +776,11 @@ static void crop_for(int in_extent, int target, int &crop_lo) {
     crop_lo = pad / 2 + pad % 2;
 }
 
+#ifndef COVA_VALIDATION
+static int simt_layer(cova_pipeline *, int) {
+    return set_err(COVA_E_UNSUPPORTED, "the validation kernels (COVA_IMPL_SIMT) are not part of this build; use libcova_b200_val.so");
+}
+#else
 static int simt_layer(cova_pipeline *p, int layer) {
     const int N = (int)p->ck_windows;
     const float *w = p->d_wraw;
@@ -797,6 +832,7 @@ static int simt_layer(cova_pipeline *p, int layer) {
     prof_mark(p, i == 0 ? "simt_dec0" : i == 1 ? "simt_dec1" : i == 2 ? "simt_dec2" : "simt_dec3_head");
     return COVA_OK;
 }
+#endif
 
 // Candidate tile configurations in order of preference; a configuration that can double-buffer its strips
 // (ring depth >= 2) beats an earlier one that cannot.
@@ -867,8 +903,8 @@ static int tc_layer(cova_pipeline *p, int layer) {
                 fp.in = p->x0f; fp.gin = p->gx0f; fp.out = p->x[1]; fp.gout = p->gx[1]; fp.N = F;
                 tc1::Enc1Extra ex;
                 memset(&ex, 0, sizeof(ex));
-                ex.n_chains = (int)p->ck_n_streams; ex.fps = (int)p->cur_fps; ex.wps = (int)windows_per_stream(p->cur_fps, p->T, p->gamma);
-                ex.gamma = (int)p->gamma; ex.first = (int)p->T - 1;
+                ex.n_chains = (int)p->ck_n_streams; ex.fps = (int)p->cur_fps; ex.wps = (int)p->cur_wps;
+                ex.gamma = (int)p->gamma; ex.first = (int)p->cur_first;
                 cudaError_t err = cudaSuccess;
                 if (tc1::try_launch_enc1(fp, ex, p->n_sms, p->stream, err)) {
                     if (err != cudaSuccess) return set_err(COVA_E_CUDA, "fused enc1 launch: %s", cudaGetErrorString(err));
@@ -886,7 +922,7 @@ static int tc_layer(cova_pipeline *p, int layer) {
             TnArgs ta;
             ta.p1 = p->p1; ta.gp1 = p->gp1; ta.x1 = p->x[1]; ta.gx1 = p->gx[1]; ta.skip = p->d[3]; ta.gskip = p->gd[3];
             ta.skip_cb = kDecCout[2] / 8; ta.newest = p->d_newest; ta.n_windows = N;
-            ta.wps = windows_per_stream(p->cur_fps, p->T, p->gamma); ta.fps = p->cur_fps; ta.gamma = p->gamma; ta.first = p->T - 1; ta.CB = kEncCout[0] / 8;
+            ta.wps = p->cur_wps; ta.fps = p->cur_fps; ta.gamma = p->gamma; ta.first = p->cur_first; ta.CB = kEncCout[0] / 8;
             memcpy(ta.w1, p->hw.enc[0].tn_w1, 64);
             memcpy(ta.w2, p->hw.enc[0].tn_w2, 64);
             long long total = (long long)ta.CB * 4 * N * p->gx[1].S;
@@ -977,7 +1013,7 @@ extern "C" int cova_pipeline_blobnet(cova_pipeline *p) {
 }
 
 static int ccl_range(cova_pipeline *p, size_t first, int n, bool reset_cursor) {
-    int rc = ccl_launch(p->ccl, p->d_mask, n, p->cc_threshold, false, p->stream, first, reset_cursor);
+    int rc = ccl_launch(p->ccl, p->d_mask, n, p->cc_threshold, false, p->stream, first, reset_cursor, !(p->dbg & kDbgNoPdl));
     if (rc) return rc;
     if (n > 0) {
         p->launches++;
@@ -1099,10 +1135,31 @@ static void use_slot(cova_pipeline *p, int k) {
 }
 static int ensure_slot(cova_pipeline *p, int k) {
     auto &sl = p->slot[k];
-    if (sl.d_frames) return COVA_OK;
-    COVA_CUDA(cudaMalloc(&sl.d_frames, p->frame_bytes * p->max_streams * p->max_fps));
-    sl.ccl.d_masks = p->d_mask;
-    return ccl_alloc(sl.ccl, (int)p->H, (int)p->W, std::max<int>(1, (int)p->max_windows), false);
+    if (sl.ready) return COVA_OK;
+    if (!sl.d_frames) COVA_CUDA(cudaMalloc(&sl.d_frames, p->frame_bytes * p->max_streams * p->max_fps));
+    if (!sl.ccl.d_blob) {
+        sl.ccl.d_masks = p->d_mask;
+        int rc = ccl_alloc(sl.ccl, (int)p->H, (int)p->W, std::max<int>(1, (int)p->max_windows), false);
+        if (rc) { ccl_free(sl.ccl, false); sl.ccl = CclBuffers(); return rc; }    // a later submit retries from scratch
+    }
+    sl.ready = true;
+    return COVA_OK;
+}
+
+// Per-stream carry-over for CONTINUED batches.  carry[id] holds the last T - 1 frames of stream `id`, newest last.
+//   mode 0 (restore): device chain s gets the newest h carried frames of stream ids[s] in front of its new frames;
+//   mode 1 (save):    the last min(fps_dev, T - 1) frames of device chain s become the carry of stream ids[s].
+__global__ void __launch_bounds__(256) carry_kernel(uint32_t *__restrict__ pool, uint32_t *__restrict__ carry, const uint32_t *__restrict__ ids,
+                                                    int n_streams, int words_per_frame, int fps_dev, int h, int t1, int mode) {
+    const int k = mode ? min(fps_dev, t1) : h;                     // frames moved per stream
+    const long long per_stream = (long long)k * words_per_frame, total = per_stream * n_streams;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(i / per_stream);
+        const long long e = i - (long long)s * per_stream;
+        uint32_t *c = carry + ((long long)ids[s] * t1 + (t1 - k)) * words_per_frame + e;
+        uint32_t *f = pool + ((long long)s * fps_dev + (mode ? fps_dev - k : 0)) * words_per_frame + e;
+        if (mode) *c = *f; else *f = *c;
+    }
 }
 
 // Host frames in, boxes out, asynchronously.  Three streams: the H2D copy of chunk c+1, the kernels of chunk c and
@@ -1110,37 +1167,145 @@ static int ensure_slot(cova_pipeline *p, int k) {
 // of one batch hide behind the kernels of another and the H2D engine is never idle.  A chunk's boxes occupy one contiguous range of the slot's device
 // arena (the cursor is only reset at the start of a batch), so each chunk needs exactly one blob copy of exactly
 // the bytes it produced.
-extern "C" int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps) {
+//
+// submit_host2 adds the stream identity the reference's elements have implicitly (one element instance per stream,
+// State.prev_buffers / gamma_idx alive for the whole stream, metapreprocess/imp.rs:38-42,302-330): with
+// COVA_SUBMIT_CONTINUE the chains of this batch continue the streams `stream_ids` from where their previous batch left
+// them - the carried T - 1 frames are put in front of the new ones on the device and the gamma phase continues, so a
+// stream cut into batches yields exactly the windows of the uncut stream.
+static int submit_impl(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, const uint32_t *stream_ids,
+                       const uint64_t *pts, uint32_t flags, bool stateful) {
     if (!p || !frames) return set_err(COVA_E_INVAL, "null argument");
+    if (flags & ~COVA_SUBMIT_CONTINUE) return set_err(COVA_E_INVAL, "unknown submit flag");
     COVA_CUDA(cudaSetDevice(p->device));
     const int k = p->next_submit;
     if (p->slot[k].busy) return set_err(COVA_E_INVAL, "four batches are already in flight: collect one first");
-    int rc = k > 0 ? ensure_slot(p, k) : COVA_OK;
+    int rc = ensure_slot(p, k);
     if (rc) return rc;
-    if ((rc = set_batch_shape(p, n_streams, fps))) return rc;
-    use_slot(p, k);
+    if (!n_streams || n_streams > p->max_streams) return set_err(COVA_E_INVAL, "batch exceeds max_streams of the pipeline");
     auto &sl = p->slot[k];
-    sl.n_streams = n_streams; sl.fps = fps; sl.n_windows = p->cur_windows; sl.busy = true;
+    const uint32_t t1 = p->T - 1;
+    uint32_t h = 0, first = t1;
+    if (stateful) {
+        if (!fps) return set_err(COVA_E_INVAL, "a stream batch needs at least one frame per stream");
+        for (uint32_t s = 0; s < n_streams; s++) {
+            const uint32_t id = stream_ids ? stream_ids[s] : s;
+            if (id >= p->max_streams) return set_err(COVA_E_INVAL, "stream id out of range (ids are 0 .. max_streams-1)");
+            for (uint32_t s2 = 0; stream_ids && s2 < s; s2++)
+                if (stream_ids[s2] == id) return set_err(COVA_E_INVAL, "a stream id appears twice in one batch");
+        }
+        if (p->n_seen.empty()) p->n_seen.assign(p->max_streams, 0);
+        if (flags & COVA_SUBMIT_CONTINUE) {
+            // the kernels take one window shape per batch: every chain must carry the same number of frames and sit at the
+            // same gamma phase, i.e. the streams of a batch advance in lock-step (start new streams in a batch of their own)
+            for (uint32_t s = 0; s < n_streams; s++) {
+                const uint64_t seen = p->n_seen[stream_ids ? stream_ids[s] : s];
+                const uint32_t hs = (uint32_t)std::min<uint64_t>(seen, t1);
+                const uint64_t base = seen - hs;                    // frames of the stream in front of the device chain
+                // smallest index i' >= T-1 of the device chain with (base + i' - (T-1)) % gamma == 0 (imp.rs:321-330)
+                const uint32_t fs = t1 + (uint32_t)((p->gamma - base % p->gamma) % p->gamma);
+                if (s == 0) { h = hs; first = fs; }
+                else if (hs != h || fs != first)
+                    return set_err(COVA_E_INVAL, "streams of one CONTINUED batch must have the same history length and gamma phase");
+            }
+        }
+        if (!p->d_carry && t1) {
+            COVA_CUDA(cudaMalloc(&p->d_carry, (size_t)p->max_streams * t1 * p->frame_bytes));
+            COVA_CUDA(cudaMemsetAsync(p->d_carry, 0, (size_t)p->max_streams * t1 * p->frame_bytes, p->stream));
+        }
+        if (!sl.h_ids) {
+            COVA_CUDA(cudaMallocHost(&sl.h_ids, sizeof(uint32_t) * p->max_streams));
+            COVA_CUDA(cudaMalloc(&sl.d_ids, sizeof(uint32_t) * p->max_streams));
+        }
+    }
+    const uint32_t fps_dev = fps + h;                               // frames per chain on the device
+    if (fps_dev > p->max_fps)
+        return set_err(COVA_E_INVAL, "carried frames + new frames exceed max_frames_per_stream of the pipeline");
+    if ((rc = set_batch_shape(p, n_streams, fps_dev, first))) return rc;
+    use_slot(p, k);
+    sl.n_streams = n_streams; sl.fps = fps_dev; sl.n_windows = p->cur_windows; sl.wps = p->cur_wps;
+    sl.win_pts.clear(); sl.win_ids.clear();
+    if (stateful) {
+        // window w of chain s has its newest frame at device index first + w*gamma = new-frame index first + w*gamma - h
+        sl.win_ids.resize(sl.n_windows);
+        if (pts) sl.win_pts.resize(sl.n_windows);
+        for (uint32_t s = 0; s < n_streams; s++) {
+            const uint32_t id = stream_ids ? stream_ids[s] : s;
+            sl.h_ids[s] = id;
+            for (uint32_t w = 0; w < sl.wps; w++) {
+                sl.win_ids[(size_t)s * sl.wps + w] = id;
+                if (pts) sl.win_pts[(size_t)s * sl.wps + w] = pts[(size_t)s * fps + (first + w * p->gamma - h)];
+            }
+            p->n_seen[id] = ((flags & COVA_SUBMIT_CONTINUE) ? p->n_seen[id] : 0) + fps;
+        }
+    }
+    sl.busy = true; sl.failed = false;
     p->next_submit = (k + 1) % kSlots;
-    if (!p->cur_windows) return COVA_OK;
+    if (!stateful && !p->cur_windows) return COVA_OK;              // chains shorter than a window: nothing to compute
+    // from here on a failure leaves the slot marked failed: the matching collect reports it instead of reading events that
+    // were never recorded
+    auto fail = [&](int code) { sl.failed = true; return code; };
+#define COVA_CUDA_SLOT(expr)                                                                                        \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess) return fail(cova::set_err(COVA_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)));    \
+    } while (0)
     const uint32_t nc = n_chunks_of(p);
-    const size_t chain_bytes = p->frame_bytes * fps;
+    const size_t src_chain = p->frame_bytes * fps, dst_chain = p->frame_bytes * fps_dev, lead = p->frame_bytes * h;
     for (uint32_t c = 0; c < nc; c++) {
         const size_t s0 = (size_t)c * p->chunk_streams, ns = std::min<size_t>(p->chunk_streams, n_streams - s0);
-        COVA_CUDA(cudaMemcpyAsync(sl.d_frames + s0 * chain_bytes, frames + s0 * chain_bytes, ns * chain_bytes, cudaMemcpyHostToDevice, p->s_in));
-        COVA_CUDA(cudaEventRecord(sl.ev_in[c], p->s_in));
+        if (!h) COVA_CUDA_SLOT(cudaMemcpyAsync(sl.d_frames + s0 * dst_chain, frames + s0 * src_chain, ns * src_chain, cudaMemcpyHostToDevice, p->s_in));
+        else COVA_CUDA_SLOT(cudaMemcpy2DAsync(sl.d_frames + s0 * dst_chain + lead, dst_chain, frames + s0 * src_chain, src_chain, src_chain, ns,
+                                              cudaMemcpyHostToDevice, p->s_in));
+        COVA_CUDA_SLOT(cudaEventRecord(sl.ev_in[c], p->s_in));
     }
+    if (stateful) COVA_CUDA_SLOT(cudaMemcpyAsync(sl.d_ids, sl.h_ids, sizeof(uint32_t) * n_streams, cudaMemcpyHostToDevice, p->stream));
+    const int wpf = (int)(p->frame_bytes / 4);
     for (uint32_t c = 0; c < nc; c++) {
-        COVA_CUDA(cudaStreamWaitEvent(p->stream, sl.ev_in[c], 0));
-        if ((rc = run_chunk(p, c))) return rc;
-        COVA_CUDA(cudaMemcpyAsync(sl.h_cursor + 2 * c, sl.ccl.d_cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
-        COVA_CUDA(cudaEventRecord(sl.ev_done[c], p->stream));
+        COVA_CUDA_SLOT(cudaStreamWaitEvent(p->stream, sl.ev_in[c], 0));
+        if (stateful && t1) {
+            const size_t s0 = (size_t)c * p->chunk_streams;
+            const int ns = (int)std::min<size_t>(p->chunk_streams, n_streams - s0);
+            uint32_t *pool = reinterpret_cast<uint32_t *>(sl.d_frames + s0 * dst_chain);
+            const int blocks = std::min(p->n_sms * 8, std::max(1, (int)(((long long)ns * t1 * wpf + 255) / 256)));
+            if (h) {
+                carry_kernel<<<blocks, 256, 0, p->stream>>>(pool, reinterpret_cast<uint32_t *>(p->d_carry), sl.d_ids + s0, ns, wpf, (int)fps_dev, (int)h, (int)t1, 0);
+                p->launches++;
+            }
+            carry_kernel<<<blocks, 256, 0, p->stream>>>(pool, reinterpret_cast<uint32_t *>(p->d_carry), sl.d_ids + s0, ns, wpf, (int)fps_dev, (int)h, (int)t1, 1);
+            p->launches++;
+            COVA_CUDA_SLOT(cudaGetLastError());
+        }
+        if (p->cur_windows) {
+            if ((rc = run_chunk(p, c))) return fail(rc);
+            COVA_CUDA_SLOT(cudaMemcpyAsync(sl.h_cursor + 2 * c, sl.ccl.d_cursor, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+        }
+        COVA_CUDA_SLOT(cudaEventRecord(sl.ev_done[c], p->stream));
+    }
+#undef COVA_CUDA_SLOT
+    return COVA_OK;
+}
+
+extern "C" int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps) {
+    return submit_impl(p, frames, n_streams, fps, nullptr, nullptr, 0, false);
+}
+extern "C" int cova_pipeline_submit_host2(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps,
+                                          const uint32_t *stream_ids, const uint64_t *pts, uint32_t flags) {
+    return submit_impl(p, frames, n_streams, fps, stream_ids, pts, flags, true);
+}
+extern "C" int cova_pipeline_reset_streams(cova_pipeline *p, const uint32_t *stream_ids, uint32_t n) {
+    if (!p) return set_err(COVA_E_INVAL, "null handle");
+    if (p->n_seen.empty()) return COVA_OK;
+    if (!stream_ids) { std::fill(p->n_seen.begin(), p->n_seen.end(), 0); return COVA_OK; }
+    for (uint32_t i = 0; i < n; i++) {
+        if (stream_ids[i] >= p->max_streams) return set_err(COVA_E_INVAL, "stream id out of range");
+        p->n_seen[stream_ids[i]] = 0;
     }
     return COVA_OK;
 }
 
-extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
-                                          uint64_t *lens, uint32_t *n_windows) {
+static int collect_impl(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens,
+                        uint32_t *n_windows, uint32_t *win_stream_ids, uint64_t *win_pts) {
     if (!p || !blob_len) return set_err(COVA_E_INVAL, "null argument");
     COVA_CUDA(cudaSetDevice(p->device));
     const int k = p->next_collect;
@@ -1150,9 +1315,22 @@ extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_
     p->next_collect = (k + 1) % kSlots;
     if (n_windows) *n_windows = sl.n_windows;
     *blob_len = 0;
-    if (!sl.n_windows) return COVA_OK;
-    const uint32_t wps = windows_per_stream(sl.fps, p->T, p->gamma);
+    if (sl.failed) {
+        sl.failed = false;
+        cudaStreamSynchronize(p->stream);
+        cudaGetLastError();
+        return set_err(COVA_E_CUDA, "the submit of this batch failed part-way; its results are void");
+    }
+    if (win_stream_ids && !sl.win_ids.empty()) memcpy(win_stream_ids, sl.win_ids.data(), sl.win_ids.size() * sizeof(uint32_t));
+    if (win_pts && !sl.win_pts.empty()) memcpy(win_pts, sl.win_pts.data(), sl.win_pts.size() * sizeof(uint64_t));
     const uint32_t nc = (sl.n_streams + p->chunk_streams - 1) / p->chunk_streams;
+    if (!sl.n_windows) {
+        // nothing to copy, but the batch's device work (carry-over of a short CONTINUED batch) must have completed before
+        // the caller may reuse its frame buffer
+        if (nc && cudaEventSynchronize(sl.ev_done[nc - 1]) != cudaSuccess) return sync_stream(p, p->stream);
+        return COVA_OK;
+    }
+    const uint32_t wps = sl.wps;
     unsigned long long prev = 0;
     bool too_small = false;
     for (uint32_t c = 0; c < nc; c++) {
@@ -1176,6 +1354,15 @@ extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_
     return COVA_OK;
 }
 
+extern "C" int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                                          uint64_t *lens, uint32_t *n_windows) {
+    return collect_impl(p, blob, blob_cap, blob_len, offsets, lens, n_windows, nullptr, nullptr);
+}
+extern "C" int cova_pipeline_collect_host2(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                                           uint64_t *lens, uint32_t *n_windows, uint32_t *win_stream_ids, uint64_t *win_pts) {
+    return collect_impl(p, blob, blob_cap, blob_len, offsets, lens, n_windows, win_stream_ids, win_pts);
+}
+
 extern "C" int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t fps, uint8_t *blob,
                                           size_t blob_cap, size_t *blob_len, uint64_t *offsets, uint64_t *lens, uint32_t *n_windows) {
     if (!p || !frames || !blob_len) return set_err(COVA_E_INVAL, "null argument");
@@ -1185,7 +1372,7 @@ extern "C" int cova_pipeline_process_host(cova_pipeline *p, const uint8_t *frame
     prof_begin(p);
     int rc = cova_pipeline_submit_host(p, frames, n_streams, fps);
     if (!rc) rc = cova_pipeline_collect_host(p, blob, blob_cap, blob_len, offsets, lens, n_windows);
-    else p->slot[0].busy = false;
+    else if (p->slot[0].busy) { p->slot[0].busy = false; p->slot[0].failed = false; p->next_submit = p->next_collect = 0; }
     if (!rc) rc = cova_pipeline_sync(p);
     return rc;
 }
@@ -1267,7 +1454,7 @@ extern "C" int cova_pipeline_read_activation(cova_pipeline *p, int layer, float 
 extern "C" int cova_pipeline_set_debug(cova_pipeline *p, int flags) {
     if (!p) return set_err(COVA_E_INVAL, "null handle");
     p->dbg = flags;
-    g_pdl = !(flags & 32);      // bit 5: plain stream-ordered launches instead of programmatic dependent launch
+    // bit 5 (kDbgNoPdl): plain stream-ordered launches instead of programmatic dependent launch, for THIS handle only
     return COVA_OK;
 }
 extern "C" int cova_pipeline_launch_count(const cova_pipeline *p, uint64_t *count) {

@@ -202,7 +202,9 @@ struct CovaSelect {
         }
         bufs.clear();
         dropped += n_dropped;
-        if (sort) {   // Tracker::flush, tracker.rs:96-125
+        // Only sink_mask_event takes and flushes the tracker (imp.rs:387-390); when the sink_enc EOS completes the pair
+        // (imp.rs:399-424) the GoP lists are drained but the still-active tracks are never written to the aggregator.
+        if (sort && which == 1) {   // Tracker::flush, tracker.rs:96-125
             const uint64_t oldest = sort->oldest_start();
             write_frames(sort->finalize(), oldest);
             sort.reset();

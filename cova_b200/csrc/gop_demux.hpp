@@ -78,23 +78,31 @@ inline int mp4_video_samples(const uint8_t *data, size_t len, std::vector<Sample
             if (memcmp(data + eb + 4, "avc1", 4) && memcmp(data + eb + 4, "avc3", 4)) return -2;
             info.width = (data[eb + 32] << 8) | data[eb + 33];
             info.height = (data[eb + 34] << 8) | data[eb + 35];
+            // the sample entry's own size field bounds the search for avcC; a malformed (oversized or undersized) entry
+            // must not send the reader past the stsd body
+            const size_t entry_size = BoxReader::be32(data + eb);
+            if (entry_size < 86) return -1;
+            const size_t entry_end = entry_size > e - eb ? e : eb + entry_size;
             size_t cb, ce;
-            if (r.find(eb + 86, eb + BoxReader::be32(data + eb), "avcC", &cb, &ce) && ce - cb >= 5) info.nal_length_size = (data[cb + 4] & 3) + 1;
+            if (r.find(eb + 86, entry_end, "avcC", &cb, &ce) && ce - cb >= 5) info.nal_length_size = (data[cb + 4] & 3) + 1;
         }
         std::vector<uint32_t> sizes;
         if (!r.find(sb, se, "stsz", &b, &e) || e - b < 12) return -1;
         {
             const uint32_t fixed = BoxReader::be32(data + b + 4), cnt = BoxReader::be32(data + b + 8);
             if (!fixed && (e - b - 12) / 4 < cnt) return -1;
+            if (cnt > len) return -1;               // every sample occupies at least one byte of the input: bounds the allocation
             sizes.resize(cnt);
             for (uint32_t i = 0; i < cnt; i++) sizes[i] = fixed ? fixed : BoxReader::be32(data + b + 12 + 4 * (size_t)i);
         }
         std::vector<uint64_t> chunk_off;
         if (r.find(sb, se, "stco", &b, &e)) {
+            if (e - b < 8) return -1;
             const uint32_t cnt = BoxReader::be32(data + b + 4);
             if ((e - b - 8) / 4 < cnt) return -1;
             for (uint32_t i = 0; i < cnt; i++) chunk_off.push_back(BoxReader::be32(data + b + 8 + 4 * (size_t)i));
         } else if (r.find(sb, se, "co64", &b, &e)) {
+            if (e - b < 8) return -1;
             const uint32_t cnt = BoxReader::be32(data + b + 4);
             if ((e - b - 8) / 8 < cnt) return -1;
             for (uint32_t i = 0; i < cnt; i++) chunk_off.push_back(BoxReader::be64(data + b + 8 + 8 * (size_t)i));

@@ -257,7 +257,12 @@ extern "C" int cova_demux_mp4_samples(const uint8_t *data, size_t len, cova_samp
     if (!data) return fail(COVA_E_INVAL, "null argument");
     std::vector<cova::host::Sample> v;
     cova::host::Mp4Info mi;
-    const int rc = cova::host::mp4_video_samples(data, len, v, mi);
+    int rc;
+    try {   // nothing throws across the C ABI: the sample tables are sized from file contents
+        rc = cova::host::mp4_video_samples(data, len, v, mi);
+    } catch (const std::bad_alloc &) {
+        return fail(COVA_E_NOMEM, "sample table too large");
+    }
     if (rc == -1) return fail(COVA_E_INVAL, "malformed or truncated ISO media file (moov / stbl)");
     if (rc == -2) return fail(COVA_E_UNSUPPORTED, "no video track with an avc1 sample entry");
     if (info) info->timescale = mi.timescale, info->width = mi.width, info->height = mi.height, info->nal_length_size = mi.nal_length_size;
@@ -266,7 +271,11 @@ extern "C" int cova_demux_mp4_samples(const uint8_t *data, size_t len, cova_samp
 extern "C" int cova_demux_annexb_frames(const uint8_t *data, size_t len, cova_sample *out, size_t out_cap, size_t *n_out) {
     if (!data && len) return fail(COVA_E_INVAL, "null argument");
     std::vector<cova::host::Sample> v;
-    cova::host::annexb_frames(data, len, v);
+    try {
+        cova::host::annexb_frames(data, len, v);
+    } catch (const std::bad_alloc &) {
+        return fail(COVA_E_NOMEM, "access-unit table too large");
+    }
     return emit_samples(v, out, out_cap, n_out);
 }
 extern "C" int cova_gopsplit_ranges(const uint32_t *flags, size_t n_frames, uint32_t n_pads, uint64_t *first_frame, uint64_t *end_frame) {

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) stack_rgba_kernel(const V *__restrict__ f
     }
 }
 
-// (b) BlobNet input layout.  Thread <-> (window n, row y, column pair x2, time t); the four t of one
+#ifdef COVA_VALIDATION
+// (b) BlobNet input layout (validation build only).  Thread <-> (window n, row y, column pair x2, time t); the four t of one
 // (y, x2) are adjacent lanes so that the 16-byte rows they write are contiguous (64 B), and a warp
 // reads 8 consecutive 8-byte pixel pairs from each of the 4 frames.
 __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__restrict__ frames,
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__res
         }
     }
 }
+
+#endif  // COVA_VALIDATION
 
 // (c) per-FRAME BlobNet input for the tcgen05 path: one 16-byte row per horizontal pixel pair,
 //     [c0 c1 c2 0 | c0' c1' c2' 0] (fp16, clipped to 6), in the two row-parity planes (ph = 0 and 2) of a

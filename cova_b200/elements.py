@@ -336,12 +336,16 @@ class BlobPipeline:
 
     def __init__(self, w_mb: int, h_mb: int, weights_blob: bytes, max_streams: int, max_frames_per_stream: int,
                  timestep: int = 4, gamma: int = 1, cc_threshold: int = 1, device: int = 0,
-                 impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False, n_chunks: int = 0):
+                 impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False, n_chunks: int = 0,
+                 validation: bool = False):
+        # validation=True (or impl=IMPL_SIMT) binds this handle to libcova_b200_val.so, the build that also holds the
+        # fp32 validation kernels; the product library refuses IMPL_SIMT
+        self._L = _lib.load_validation() if (validation or impl == _lib.IMPL_SIMT) else _lib.load()
         self._h = ctypes.c_void_p()
         flags = impl | (_lib.FLAG_KEEP_LOGITS if keep_logits else 0) | (_lib.FLAG_KEEP_STACKED if keep_stacked else 0)
         flags |= (n_chunks & 0xff) << 16
         self._wbuf = ctypes.create_string_buffer(weights_blob, len(weights_blob))
-        check(_lib.load().cova_pipeline_new(ctypes.byref(self._h), device, w_mb, h_mb, timestep, gamma, max_streams,
+        self._check(self._L.cova_pipeline_new(ctypes.byref(self._h), device, w_mb, h_mb, timestep, gamma, max_streams,
                                             max_frames_per_stream, ctypes.cast(self._wbuf, ctypes.c_void_p),
                                             len(weights_blob), cc_threshold, flags))
         self.w_mb, self.h_mb, self.timestep, self.gamma = w_mb, h_mb, timestep, gamma
@@ -349,18 +353,21 @@ class BlobPipeline:
         self.n_windows = 0
         self._blob = None
 
+    def _check(self, rc: int) -> int:
+        return check(rc, self._L)
+
     # ---- configuration
     def set_property(self, name: str, value: int):
         if name != "cc-threshold":
             raise KeyError(name)
-        check(_lib.load().cova_pipeline_set_cc_threshold(self._h, value))
+        self._check(self._L.cova_pipeline_set_cc_threshold(self._h, value))
 
     def set_stream(self, cuda_stream: int | None):
-        check(_lib.load().cova_pipeline_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+        self._check(self._L.cova_pipeline_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
     def windows_for(self, n_streams: int, frames_per_stream: int) -> int:
         n = ctypes.c_uint32()
-        check(_lib.load().cova_pipeline_n_windows(self._h, n_streams, frames_per_stream, ctypes.byref(n)))
+        self._check(self._L.cova_pipeline_n_windows(self._h, n_streams, frames_per_stream, ctypes.byref(n)))
         return n.value
 
     # ---- stages
@@ -371,9 +378,9 @@ class BlobPipeline:
             n_streams, frames_per_stream = a.shape[0], a.shape[1]
             assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
             self._keep = a
-            check(_lib.load().cova_pipeline_load_frames(self._h, _ptr(a), n_streams, frames_per_stream, 0))
+            self._check(self._L.cova_pipeline_load_frames(self._h, _ptr(a), n_streams, frames_per_stream, 0))
         else:
-            check(_lib.load().cova_pipeline_load_frames(self._h, ctypes.c_void_p(int(frames)), n_streams, frames_per_stream, 1))
+            self._check(self._L.cova_pipeline_load_frames(self._h, ctypes.c_void_p(int(frames)), n_streams, frames_per_stream, 1))
         self.n_windows = self.windows_for(n_streams, frames_per_stream)
 
     def load_masks(self, masks, n: int | None = None):
@@ -381,28 +388,28 @@ class BlobPipeline:
             a = np.ascontiguousarray(masks, dtype=np.uint8)
             n = a.shape[0]
             self._keep = a
-            check(_lib.load().cova_pipeline_load_masks(self._h, _ptr(a), n, 0))
+            self._check(self._L.cova_pipeline_load_masks(self._h, _ptr(a), n, 0))
         else:
-            check(_lib.load().cova_pipeline_load_masks(self._h, ctypes.c_void_p(int(masks)), n, 1))
+            self._check(self._L.cova_pipeline_load_masks(self._h, ctypes.c_void_p(int(masks)), n, 1))
         self.n_windows = n
 
     def tensorise(self):
-        check(_lib.load().cova_pipeline_tensorise(self._h))
+        self._check(self._L.cova_pipeline_tensorise(self._h))
 
     def blobnet(self):
-        check(_lib.load().cova_pipeline_blobnet(self._h))
+        self._check(self._L.cova_pipeline_blobnet(self._h))
 
     def run_layer(self, layer: int, impl: int):
-        check(_lib.load().cova_pipeline_run_layer(self._h, layer, impl))
+        self._check(self._L.cova_pipeline_run_layer(self._h, layer, impl))
 
     def ccl(self):
-        check(_lib.load().cova_pipeline_ccl(self._h))
+        self._check(self._L.cova_pipeline_ccl(self._h))
 
     def run(self):
-        check(_lib.load().cova_pipeline_run(self._h))
+        self._check(self._L.cova_pipeline_run(self._h))
 
     def sync(self):
-        check(_lib.load().cova_pipeline_sync(self._h))
+        self._check(self._L.cova_pipeline_sync(self._h))
 
     def fetch_boxes_raw(self, blob_cap: int | None = None):
         """(blob, offsets, lens): window i's bincode(Vec<Bbox>) is blob[offsets[i] : offsets[i] + lens[i]].
@@ -411,7 +418,7 @@ class BlobPipeline:
         cap = blob_cap or n * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
         self._ensure_out(cap)
         ln = ctypes.c_size_t()
-        check(_lib.load().cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln),
+        self._check(self._L.cova_pipeline_fetch_boxes(self._h, _ptr(self._blob), self._blob.size, ctypes.byref(ln),
                                                     _ptr(self._offs), _ptr(self._lens)))
         self.last_blob_len = ln.value
         return self._blob, self._offs[:n], self._lens[:n]
@@ -426,29 +433,57 @@ class BlobPipeline:
         return n_windows * (8 + 24 * ((self.h_mb + 1) // 2) * ((self.w_mb + 1) // 2))
 
     # ---- asynchronous streaming form: at most four batches in flight
-    def submit(self, frames: np.ndarray, blob_cap: int | None = None):
+    def submit(self, frames: np.ndarray, blob_cap: int | None = None, stream_ids=None, pts=None, cont: bool | None = None):
         """Enqueue one batch (copies + kernels) and return immediately.  `frames` should live in page-locked
-        memory (PinnedBuffer) and must stay untouched until the matching collect()."""
+        memory (PinnedBuffer) and must stay untouched until the matching collect().
+
+        With `stream_ids` / `pts` / `cont` the batch goes through cova_pipeline_submit_host2: chain s belongs to stream
+        stream_ids[s] (default 0, 1, ...), `pts[s, f]` is echoed per window by collect(meta=True), and cont=True continues
+        the streams from their previous batch (carried timestep-1 frames + gamma phase) like one long-lived metapreprocess
+        element would."""
         a = np.ascontiguousarray(frames, dtype=np.uint8)
         assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
-        self._ensure_out(blob_cap or self._worst_case_cap(self.windows_for(a.shape[0], a.shape[1])))
-        check(_lib.load().cova_pipeline_submit_host(self._h, _ptr(a), a.shape[0], a.shape[1]))
+        if stream_ids is None and pts is None and cont is None:
+            self._ensure_out(blob_cap or self._worst_case_cap(self.windows_for(a.shape[0], a.shape[1])))
+            self._check(self._L.cova_pipeline_submit_host(self._h, _ptr(a), a.shape[0], a.shape[1]))
+        else:
+            # a continued chain can emit one window per new frame
+            self._ensure_out(blob_cap or self._worst_case_cap(a.shape[0] * a.shape[1]))
+            ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.uint32)
+            p = None if pts is None else np.ascontiguousarray(pts, dtype=np.uint64)
+            assert ids is None or ids.shape == (a.shape[0],)
+            assert p is None or p.shape == a.shape[:2]
+            self._check(self._L.cova_pipeline_submit_host2(self._h, _ptr(a), a.shape[0], a.shape[1], None if ids is None else _ptr(ids),
+                                                         None if p is None else _ptr(p), _lib.SUBMIT_CONTINUE if cont else 0))
         self._inflight = getattr(self, "_inflight", []) + [a]
 
-    def collect(self, raw: bool = False):
-        """Wait for the oldest submitted batch; same return value as process()."""
+    def reset_streams(self, stream_ids=None):
+        if stream_ids is None:
+            self._check(self._L.cova_pipeline_reset_streams(self._h, None, 0))
+        else:
+            ids = np.ascontiguousarray(stream_ids, dtype=np.uint32)
+            self._check(self._L.cova_pipeline_reset_streams(self._h, _ptr(ids), ids.size))
+
+    def collect(self, raw: bool = False, meta: bool = False):
+        """Wait for the oldest submitted batch; same return value as process().  meta=True (batches submitted with
+        stream_ids / pts): returns (result, window_stream_ids, window_pts) through cova_pipeline_collect_host2."""
         k = getattr(self, "_collect_idx", 0)
         self._collect_idx = k ^ 1
         blob, offs, lens = (b.array for b in self._pin[k])
         ln, nw = ctypes.c_size_t(), ctypes.c_uint32()
-        check(_lib.load().cova_pipeline_collect_host(self._h, _ptr(blob), blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens),
-                                                     ctypes.byref(nw)))
+        if meta:
+            wid, wpts = np.zeros(offs.size, dtype=np.uint32), np.zeros(offs.size, dtype=np.uint64)
+            rc = self._L.cova_pipeline_collect_host2(self._h, _ptr(blob), blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens),
+                                                         ctypes.byref(nw), _ptr(wid), _ptr(wpts))
+        else:
+            rc = self._L.cova_pipeline_collect_host(self._h, _ptr(blob), blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens),
+                                                        ctypes.byref(nw))
         self._inflight.pop(0)
+        self._check(rc)
         self.n_windows, self.last_blob_len = nw.value, ln.value
         n = nw.value
-        if raw:
-            return blob, offs[:n], lens[:n]
-        return [blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs[:n], lens[:n])]
+        res = (blob, offs[:n], lens[:n]) if raw else [blob[int(o): int(o) + int(l)].tobytes() for o, l in zip(offs[:n], lens[:n])]
+        return (res, wid[:n], wpts[:n]) if meta else res
 
     def fetch_boxes(self) -> list[bytes]:
         blob, offs, lens = self.fetch_boxes_raw()
@@ -464,7 +499,7 @@ class BlobPipeline:
         self._ensure_out(blob_cap or self._worst_case_cap(n))
         self._collect_idx = 0
         ln, nw = ctypes.c_size_t(), ctypes.c_uint32()
-        check(_lib.load().cova_pipeline_process_host(self._h, _ptr(a), n_streams, fps, _ptr(self._blob), self._blob.size,
+        self._check(self._L.cova_pipeline_process_host(self._h, _ptr(a), n_streams, fps, _ptr(self._blob), self._blob.size,
                                                      ctypes.byref(ln), _ptr(self._offs), _ptr(self._lens), ctypes.byref(nw)))
         self.n_windows, self.last_blob_len = nw.value, ln.value
         if raw:
@@ -474,49 +509,49 @@ class BlobPipeline:
     # ---- inspection (parity tests)
     def read_stacked(self) -> np.ndarray:
         out = np.empty((self.n_windows, self.timestep * self.h_mb, self.w_mb, 4), dtype=np.uint8)
-        check(_lib.load().cova_pipeline_read_stacked(self._h, _ptr(out), out.size))
+        self._check(self._L.cova_pipeline_read_stacked(self._h, _ptr(out), out.size))
         return out
 
     def read_mask(self) -> np.ndarray:
         out = np.empty((self.n_windows, self.h_mb, self.w_mb), dtype=np.uint8)
-        check(_lib.load().cova_pipeline_read_mask(self._h, _ptr(out), out.size))
+        self._check(self._L.cova_pipeline_read_mask(self._h, _ptr(out), out.size))
         return out
 
     def read_logits(self) -> np.ndarray:
         out = np.empty((self.n_windows, self.h_mb, self.w_mb), dtype=np.float32)
-        check(_lib.load().cova_pipeline_read_logits(self._h, _ptr(out), out.size))
+        self._check(self._L.cova_pipeline_read_logits(self._h, _ptr(out), out.size))
         return out
 
     def read_activation(self, layer: int) -> np.ndarray:
         cap = self.n_windows * 128 * 4 * self.h_mb * self.w_mb
         out = np.empty(cap, dtype=np.float32)
         shape = (ctypes.c_uint32 * 5)()
-        check(_lib.load().cova_pipeline_read_activation(self._h, layer, _ptr(out), out.size, shape))
+        self._check(self._L.cova_pipeline_read_activation(self._h, layer, _ptr(out), out.size, shape))
         shp = tuple(int(v) for v in shape)
         return out[: int(np.prod(shp))].reshape(shp).copy()
 
     def set_debug(self, flags: int):
-        check(_lib.load().cova_pipeline_set_debug(self._h, flags))
+        self._check(self._L.cova_pipeline_set_debug(self._h, flags))
 
     def launch_count(self) -> int:
         c = ctypes.c_uint64()
-        check(_lib.load().cova_pipeline_launch_count(self._h, ctypes.byref(c)))
+        self._check(self._L.cova_pipeline_launch_count(self._h, ctypes.byref(c)))
         return c.value
 
     def set_profiling(self, enable: bool):
-        check(_lib.load().cova_pipeline_set_profiling(self._h, int(enable)))
+        self._check(self._L.cova_pipeline_set_profiling(self._h, int(enable)))
 
     def last_timings(self) -> dict[str, float]:
         names = ctypes.create_string_buffer(1024)
         ms = (ctypes.c_float * 64)()
         n = ctypes.c_uint32(64)
-        check(_lib.load().cova_pipeline_last_timings(self._h, names, 1024, ms, ctypes.byref(n)))
+        self._check(self._L.cova_pipeline_last_timings(self._h, names, 1024, ms, ctypes.byref(n)))
         keys = names.value.decode().split(";") if names.value else []
         return {k: float(ms[i]) for i, k in enumerate(keys)}
 
     def close(self):
         if self._h:
-            _lib.load().cova_pipeline_free(self._h)
+            self._L.cova_pipeline_free(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

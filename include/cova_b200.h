@@ -102,7 +102,8 @@ int cova_bboxcc_labels(cova_bboxcc *cc, const uint8_t *mask, size_t mask_len, in
  *
  * A batch is n_streams independent chains of frames_per_stream consecutive frames each, every chain
  * starting with an empty window exactly like a freshly started element (gopsplit hands every chain
- * whole GoPs, gst-plugins/gst-gopsplit/gstgopsplit.cpp:557-630).  Windows are emitted in stream-major,
+ * whole GoPs, gst-plugins/gst-gopsplit/gstgopsplit.cpp:557-630); cova_pipeline_submit_host2 below continues
+ * named streams across batches instead.  Windows are emitted in stream-major,
  * time-minor order; window w of a stream is the one whose newest frame is (timestep-1) + w*gamma.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct cova_pipeline cova_pipeline;
@@ -151,6 +152,31 @@ int cova_pipeline_submit_host(cova_pipeline *p, const uint8_t *frames, uint32_t 
 int cova_pipeline_collect_host(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
                                uint64_t *lens, uint32_t *n_windows);
 
+/* Stream continuity (metapreprocess/imp.rs:38-42,302-330: State.prev_buffers and gamma_idx live for the whole stream; an
+ * element instance never restarts its window between buffers).  submit_host / process_host treat every chain of every
+ * batch as a freshly started element - right for GoP shards, each of which the reference also feeds to a fresh chain
+ * (gstgopsplit.cpp:557-630), but a stream that is fed in SEVERAL batches would lose timestep-1 windows at every seam
+ * and shift its gamma phase.  submit_host2 names the streams:
+ *   stream_ids[n_streams]  ids in [0, max_streams), distinct within a batch; NULL = 0, 1, 2, ...
+ *   pts[n_streams * frames_per_stream]  optional presentation time of every frame, echoed per window by collect_host2
+ *   flags  COVA_SUBMIT_CONTINUE: chain s continues stream stream_ids[s]: the last timestep-1 frames of the stream (kept on
+ *          the device) precede the new ones and the gamma phase carries on, so the batch yields exactly the windows the
+ *          uncut stream would have produced for these frames (frames_per_stream windows per chain at gamma 1).
+ *          Without the flag the named streams (re)start with an empty window.  Either way their state is recorded.
+ * Constraints: the streams of one CONTINUED batch must advance in lock-step (same number of frames seen so far modulo
+ * nothing: same history length min(seen, timestep-1) and same gamma phase) - COVA_E_INVAL otherwise; carried + new
+ * frames must fit max_frames_per_stream.  Window order stays stream-major, time-minor.
+ * collect_host2: as collect_host, plus per window the stream id and the PTS of its newest frame (the PTS the
+ * reference's metapreprocess output buffer carries, BaseTransform default; cova/imp.rs:110-112 requires it).
+ * Both arrays have n_windows entries; win_pts is only written when the submit passed pts. */
+#define COVA_SUBMIT_CONTINUE 1u
+int cova_pipeline_submit_host2(cova_pipeline *p, const uint8_t *frames, uint32_t n_streams, uint32_t frames_per_stream,
+                               const uint32_t *stream_ids, const uint64_t *pts, uint32_t flags);
+int cova_pipeline_collect_host2(cova_pipeline *p, uint8_t *blob, size_t blob_cap, size_t *blob_len, uint64_t *offsets,
+                                uint64_t *lens, uint32_t *n_windows, uint32_t *win_stream_ids, uint64_t *win_pts);
+/* forget the state of the given streams (NULL = all): their next CONTINUED batch starts with an empty window */
+int cova_pipeline_reset_streams(cova_pipeline *p, const uint32_t *stream_ids, uint32_t n);
+
 /* feed a mask batch straight to the CCL stage (u8 [n][h_mb][w_mb]; is_device as above) */
 int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, uint32_t n, int is_device);
 
@@ -168,7 +194,7 @@ int cova_pipeline_run_layer(cova_pipeline *p, int layer, uint32_t impl);
 /* development switches.  Results become garbage with bit 0 (skip the MMAs) or bit 1 (skip the epilogue math); the others
  * select alternative, equally correct code paths for A/B measurements (tools/ab_step.py, tools/layer_timing.py):
  * bit 2 positions-as-M kernels for encoder blocks 2 and 4, bit 3 weights-stationary kernel for block 3, bit 4 two-kernel
- * block 1, bit 5 plain stream-ordered launches instead of programmatic dependent launch (process-wide), bit 6 whole-tile
+ * block 1, bit 5 plain stream-ordered launches instead of programmatic dependent launch (this handle only), bit 6 whole-tile
  * accumulators for dec0 / dec1 */
 int cova_pipeline_set_debug(cova_pipeline *p, int flags);
 /* kernels launched by this handle since creation */

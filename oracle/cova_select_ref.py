@@ -155,7 +155,9 @@ class CovaSelectRef:
             self.dropped += len(g[2])
             pushed += [(b[0], b[1], b[2], n_lists) for b in g[3]] or [(EMPTY_LIST, 0, 0, n_lists)]
         self.bufs = []
-        if self.sort is not None:
+        # imp.rs:387-390 vs 399-424: only the sink_mask event handler takes and flushes the tracker; a sink_enc EOS that
+        # arrives second drains the GoP lists and leaves the active tracks unwritten
+        if self.sort is not None and pad == 1:
             oldest = self.sort.oldest_start()
             self._write_frames(self.sort.finalize(), oldest)
             self.sort = None

@@ -120,3 +120,28 @@ def test_old_gops_are_dropped_after_250_frames():
     s.eos(0)
     assert len(s.eos(1)) == 5 and s.get_property("dropped") == 400
     assert s.get_property("decoded-inference") == 0 and s.get_property("decoded-dependency") == 0
+
+
+def test_eos_pad_order_decides_whether_the_tracker_is_flushed():
+    """Only sink_mask_event takes and flushes the tracker (imp.rs:387-390).  When the sink_enc EOS is the one that
+    completes the pair (imp.rs:399-424) the GoP lists are still drained, but the tracks alive at EOS never reach the
+    aggregator - a reference quirk both implementations must share."""
+    props = dict(sort_maxage=6, sort_minhits=10, sort_iou=0.1, port=7000)
+    frames = moving_boxes(4, 200, 4, drop=0.0, clutter=0.0)
+    wires = {}
+    for first_pad in (0, 1):
+        got, ref = CovaSelect(**props), CovaSelectRef(**props)
+        for f, (_, bx) in enumerate(frames):
+            got.sink_enc(f, f * FRAME_NS, 0 if f % 50 == 0 else 1)
+            ref.sink_enc(f, f * FRAME_NS, 0 if f % 50 == 0 else 1)
+            boxes = [sort_ref.bbox(*b) for b in bx]
+            a = got.sink_mask(serialize_vec([b[:5] for b in boxes]), f * FRAME_NS)
+            b = ref.sink_mask(boxes, f * FRAME_NS)
+            assert [tuple(int(v) for v in p) for p in a] == [tuple(int(v) for v in p) for p in b]
+        assert got.eos(first_pad) is None and ref.on_eos(first_pad) is None
+        a, b = got.eos(1 - first_pad), ref.on_eos(1 - first_pad)
+        assert [tuple(int(v) for v in p) for p in a] == [tuple(int(v) for v in p) for p in b]
+        wires[first_pad] = (split_wire(got.take_wire()), split_wire(bytes(ref.wire)))
+        assert len(wires[first_pad][0]) == len(wires[first_pad][1])
+    # sink_enc first, sink_mask second: flushed -> strictly more Frame records than in the other order
+    assert len(wires[0][0]) > len(wires[1][0])

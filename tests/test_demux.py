@@ -107,3 +107,50 @@ def test_annexb_scan_recovers_the_real_clip():
     assert got == demux_ref.annexb_frames(bytes(stream))
     assert [g[0] for g in got] == starts
     assert [g[2] for g in got] == [s[2] for s in samples]
+
+
+def test_malformed_mp4_never_reads_out_of_bounds_or_aborts():
+    """The parser is driven by file contents: an oversized avc1 sample-entry size, stco / co64 / stsc bodies shorter than
+    their headers, a 4-billion-entry fixed-size stsz and random corruption must all come back as an error code (or a
+    valid table) - run in a child process so that a crash is a test failure, not the end of the session."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, struct
+import numpy as np
+sys.path.insert(0, %r)
+from cova_b200 import _lib, shard
+moov = bytearray(open(%r, "rb").read())
+def attempt(buf):
+    try:
+        shard.demux_mp4(bytes(buf))
+    except _lib.CovaError as e:
+        assert e.code in (_lib.E_INVAL, _lib.E_UNSUPPORTED, _lib.E_NOMEM), e.code
+def box(tag):
+    i = bytes(moov).find(tag)
+    assert i >= 4
+    return i - 4
+# (1) avc1 sample entry claiming to be 4 GB / 0 bytes long
+i = box(b"stsd") + 16
+for v in (0xFFFFFFF0, 0, 40):
+    m = bytearray(moov); m[i:i + 4] = struct.pack(">I", v); attempt(m)
+# (2) stco / stsc / stsz truncated to less than their fixed header, (3) absurd counts
+for tag in (b"stco", b"stsc", b"stsz", b"stts", b"ctts", b"stss"):
+    i = box(tag)
+    for sz in (8, 10, 12, 15):
+        m = bytearray(moov); m[i:i + 4] = struct.pack(">I", sz); attempt(m)
+    m = bytearray(moov); m[i + 12:i + 16] = b"\xff\xff\xff\xff"; attempt(m)
+    m = bytearray(moov); m[i + 16:i + 20] = b"\xff\xff\xff\xff"; attempt(m)
+i = box(b"stsz")
+m = bytearray(moov); m[i + 12:i + 16] = struct.pack(">I", 1000); m[i + 16:i + 20] = b"\xff\xff\xff\xf0"; attempt(m)   # fixed size, 4e9 samples
+# (4) random corruption and truncation
+rng = np.random.default_rng(0)
+for _ in range(300):
+    m = bytearray(moov)
+    for _ in range(int(rng.integers(1, 8))):
+        m[int(rng.integers(0, len(m)))] = int(rng.integers(0, 256))
+    attempt(m[: int(rng.integers(16, len(m) + 1))] if rng.random() < 0.3 else m)
+print("ok")
+''' % (os.path.dirname(HERE), os.path.join(HERE, "golden", "demo_1m_moov.bin"))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout[-300:], r.stderr[-800:])

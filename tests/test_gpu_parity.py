@@ -399,3 +399,119 @@ def test_bind_rank_to_gpu_keeps_the_process_inside_its_cpu_set():
         assert info["numa_node"] >= -1
     finally:
         os.sched_setaffinity(0, before)
+
+
+# ----------------------------------------------------------------------------------------- stream continuity (submit_host2)
+@pytest.mark.parametrize("gamma,cuts", [(1, (30, 37)), (3, (30, 37)), (1, (2, 1, 5, 30, 29)), (2, (1, 1, 1, 1, 33, 30)), (3, (4, 63))])
+def test_stream_cut_into_batches_equals_the_uncut_stream(gamma, cuts):
+    """One long-lived metapreprocess element keeps prev_buffers and gamma_idx for the whole stream (imp.rs:38-42,302-330).
+    A 67-frame stream submitted in pieces with COVA_SUBMIT_CONTINUE must return byte-identical boxes, stacked tensors
+    and masks, window for window, to the single submit - none lost at the seams, gamma phase intact - and echo the PTS of
+    every window's newest frame."""
+    assert sum(cuts) == 67
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.synth_streams(3, 67, 45, 80, config_idx=12)
+    pts = (np.arange(3 * 67, dtype=np.uint64).reshape(3, 67) * np.uint64(33_366_667)) + np.uint64(5)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 3, 67, gamma=gamma, keep_stacked=True)
+    whole = p.process(frames)
+    whole_mask, whole_stacked = p.read_mask(), p.read_stacked()
+    wps = len(whole) // 3
+    assert wps == (67 - 4) // gamma + 1
+    ids = np.array([2, 0, 1], dtype=np.uint32)
+    per_stream = {int(i): [] for i in ids}
+    masks = {int(i): [] for i in ids}
+    stacks = {int(i): [] for i in ids}
+    got_pts = {int(i): [] for i in ids}
+    lo = 0
+    for k, n in enumerate(cuts):
+        p.submit(frames[:, lo: lo + n], stream_ids=ids, pts=pts[:, lo: lo + n], cont=k > 0)
+        boxes, wid, wpts = p.collect(meta=True)
+        lo += n
+        if not len(boxes):
+            continue
+        m, st = p.read_mask(), p.read_stacked()
+        w = len(boxes) // 3
+        assert (wid == np.repeat(ids, w)).all()
+        for s, sid in enumerate(ids):
+            per_stream[int(sid)] += boxes[s * w: (s + 1) * w]
+            masks[int(sid)].append(m[s * w: (s + 1) * w])
+            stacks[int(sid)].append(st[s * w: (s + 1) * w])
+            got_pts[int(sid)] += wpts[s * w: (s + 1) * w].tolist()
+    for s, sid in enumerate(ids):
+        assert per_stream[int(sid)] == whole[s * wps: (s + 1) * wps], (gamma, cuts, s)
+        assert (np.concatenate(masks[int(sid)]) == whole_mask[s * wps: (s + 1) * wps]).all()
+        assert (np.concatenate(stacks[int(sid)]) == whole_stacked[s * wps: (s + 1) * wps]).all()
+        assert got_pts[int(sid)] == [int(pts[s, 3 + w * gamma]) for w in range(wps)]
+    # and it is what the element shim (one instance per stream) emits for the same stream
+    el = MetaPreprocess(1280, 720, 4, gamma)
+    outs = [o for f in range(67) for rc, o in [el.transform(frames[1, f])] if rc == FLOW_OK]
+    assert len(outs) == wps and all(np.frombuffer(o, np.uint8).tobytes() == whole_stacked[wps + i].tobytes() for i, o in enumerate(outs))
+
+
+def test_stream_continuity_rules_and_restart():
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.synth_streams(2, 12, 45, 80, config_idx=13)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 4, 12)
+    fresh = p.process(frames)                                        # 2 x 9 windows
+    # not continued: named streams restart with an empty window, exactly like submit_host
+    p.submit(frames, stream_ids=[3, 1]); assert p.collect() == fresh
+    p.submit(frames, stream_ids=[3, 1]); assert p.collect() == fresh
+    # continued after 12 frames: 3 carried + 9 new frames fit max_frames_per_stream = 12 -> 9 windows per chain
+    p.submit(frames[:, :9], stream_ids=[3, 1], cont=True)
+    assert len(p.collect()) == 2 * 9
+    # stream 0 has no history, stream 3 has: not in lock-step
+    with pytest.raises(_lib.CovaError) as e:
+        p.submit(frames[:, :4], stream_ids=[0, 3], cont=True)
+    assert e.value.code == _lib.E_INVAL
+    with pytest.raises(_lib.CovaError):                              # 3 carried + 12 new > max_frames_per_stream
+        p.submit(frames, stream_ids=[3, 1], cont=True)
+    with pytest.raises(_lib.CovaError):
+        p.submit(frames, stream_ids=[1, 1])                          # duplicate id
+    with pytest.raises(_lib.CovaError):
+        p.submit(frames, stream_ids=[0, 4])                          # id out of range
+    # after a reset a continued batch starts empty again
+    p.reset_streams([3, 1])
+    p.submit(frames, stream_ids=[3, 1], cont=True)
+    assert p.collect() == fresh
+    assert p.process(frames) == fresh                                # the plain entry points are unaffected
+
+
+# ----------------------------------------------------------------------------------------- re-entrancy across handles
+def test_two_threads_two_handles_and_mixed_resolutions():
+    """include/cova_b200.h promises that different handles may be used concurrently from different threads (one GStreamer
+    streaming thread per chain, metapreprocess/imp.rs:45-48).  Two pipelines of DIFFERENT grids (the 1080p CCL needs more
+    than the default 48 KB of dynamic shared memory, the 720p one does not - a function attribute shared by all handles)
+    and two bboxcc elements hammer the library from two threads; a debug switch flipped on one handle must not leak into
+    the other."""
+    import threading
+    wts = weights.random_weights(0, head_bias=-1.0)
+    blob = weights.to_blob(wts)
+    cfg = [(45, 80, 3, 9), (68, 120, 2, 7)]
+    pipes, frames, want, els, masks, want_cc = [], [], [], [], [], []
+    for h, w, ns, fps in cfg:
+        p = BlobPipeline(w, h, blob, ns, fps)
+        f = synth.synth_streams(ns, fps, h, w, config_idx=20 + h)
+        pipes.append(p); frames.append(f); want.append(p.process(f))
+        el = BboxCc(w, h, 1)
+        m = synth.mask_patterns(h, w, seed=h)["bernoulli_0.4"]
+        els.append(el); masks.append(m); want_cc.append(bboxcc_ref.bboxcc_transform_ref(m, w, h, 1))
+    assert els[1].transform_ip(masks[1]) == want_cc[1]               # 1080p after a 720p handle was created and used
+    assert els[0].transform_ip(masks[0]) == want_cc[0]
+    assert els[1].transform_ip(masks[1]) == want_cc[1]
+    pipes[1].set_debug(32)                                           # plain launches on handle 1 only
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(25):
+                assert pipes[i].process(frames[i]) == want[i]
+                assert els[i].transform_ip(masks[i]) == want_cc[i]
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors

@@ -96,3 +96,29 @@ def test_synthetic_stream_statistics():
     assert (fr[:, 0, :, :, 0] == 6).all()                  # frame 0 is the IDR: all intra
     assert fr[..., 3].max() <= 4                           # stale byte
     assert (fr[:, 1:, :, :, 0] == 1).mean() > 0.8          # mostly skip MBs
+
+
+def test_validation_kernels_are_not_in_the_shipped_library():
+    """libcova_b200.so holds the hot path only: it refuses COVA_IMPL_SIMT; libcova_b200_val.so (same sources,
+    -DCOVA_VALIDATION) is the build the layer-by-layer parity tests load.  Both export the whole ABI."""
+    blob = weights.to_blob(weights.random_weights(0))
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    h = ctypes.c_void_p()
+    prod, val = _lib.load(), _lib.load_validation()
+    assert prod is not val
+    rc = prod.cova_pipeline_new(ctypes.byref(h), 0, 80, 45, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1, _lib.IMPL_SIMT)
+    assert rc == _lib.E_UNSUPPORTED and b"libcova_b200_val.so" in prod.cova_last_error()
+    rc = val.cova_pipeline_new(ctypes.byref(h), 0, 80, 45, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1, _lib.IMPL_SIMT)
+    assert rc in (_lib.OK, _lib.E_NODEVICE)                # accepted; fails later only for want of a device
+    if rc == _lib.OK:
+        val.cova_pipeline_free(h)
+    for name in _lib.SIGNATURES:
+        assert hasattr(val, name)
+
+
+def test_stream_batch_argument_validation():
+    lib = _lib.load()
+    assert lib.cova_pipeline_submit_host2(None, None, 1, 1, None, None, 0) == _lib.E_INVAL
+    n = ctypes.c_size_t()
+    assert lib.cova_pipeline_collect_host2(None, None, 0, ctypes.byref(n), None, None, None, None, None) == _lib.E_INVAL
+    assert lib.cova_pipeline_reset_streams(None, None, 0) == _lib.E_INVAL
