@@ -478,7 +478,8 @@ class BlobPipeline:
         else:
             rc = self._L.cova_pipeline_collect_host(self._h, _ptr(blob), blob.size, ctypes.byref(ln), _ptr(offs), _ptr(lens),
                                                         ctypes.byref(nw))
-        self._inflight.pop(0)
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
         self._check(rc)
         self.n_windows, self.last_blob_len = nw.value, ln.value
         n = nw.value

@@ -15,11 +15,35 @@ G = np.load(os.path.join(HERE, "golden", "ccl_golden.npz"))
 META = [m.split(",") for m in G["meta"]]
 
 # floating-point bars (BASELINE.json north_star): logits within fp16 tolerance of the fp32 oracle and at
-# most 0.1 % of mask pixels flipping.  fp16 operands / fp32 accumulation over 8 layers: 2e-2 of the
-# logit scale is ~25x the error actually observed.
-LOGIT_REL_TOL = 2e-2
-ACT_REL_TOL = 1e-2
+# most 0.1 % of mask pixels flipping.  fp16 operands (11-bit significand: 4.9e-4 relative per rounding) with fp32
+# accumulation over 8 layers: the observed worst case over every test below is 9.5e-4 of the logit scale and 9.9e-4 of a
+# layer's activation scale (profiles/r2_parity_errors.txt, written with COVA_PARITY_LOG), so the bars sit at 4-5x that, not 20x.
+LOGIT_REL_TOL = 5e-3
+ACT_REL_TOL = 4e-3
 MAX_FLIP = 1e-3
+ERRLOG = os.environ.get("COVA_PARITY_LOG")          # optional: append the observed errors of every comparison
+
+
+def _log(tag, **kv):
+    if ERRLOG:
+        with open(ERRLOG, "a") as f:
+            f.write(tag + " " + " ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in kv.items()) + "\n")
+
+
+def _check_windows_against_oracle(tag, wts, p, frames, windows, wps, gamma=1):
+    """Oracle logits + masks on a SAMPLE of windows of a large batch: window k of chain s is rebuilt from the host frames,
+    run through the fp32 oracle and compared with what the device produced for it."""
+    logits, mask, stacked = p.read_logits(), p.read_mask(), p.read_stacked()
+    want_stacked = np.stack([mpr.tensorise_stream(frames[k // wps], 4, gamma)[k % wps] for k in windows])
+    assert (stacked[windows] == want_stacked).all()
+    ref = blobnet_ref.blobnet_forward(wts, mpr.stacked_to_nchw(want_stacked, 4))
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(logits[windows] - ref).max())
+    flips = float(((logits[windows] > 0) != (ref > 0)).mean())
+    _log(tag, windows=len(windows), logit_err_rel=err / scale, flips=flips)
+    assert err <= LOGIT_REL_TOL * scale, (tag, err, scale)
+    assert flips <= MAX_FLIP, (tag, flips)
+    assert (mask[windows] == (logits[windows] > 0)).all()
 
 
 def golden_case(i):
@@ -144,8 +168,11 @@ def test_tensorise_and_blobnet_against_oracle(h, w, n_streams, fps, seed):
         a = p.read_activation(layer)
         assert a.shape == refs[layer].shape
         err = np.abs(a - refs[layer]).max() / (np.abs(refs[layer]).max() + 1e-12)
+        _log(f"oracle_{h}x{w}", layer=layer, act_err_rel=float(err))
         assert err < ACT_REL_TOL, (layer, err)
     logits, mask = p.read_logits(), p.read_mask()
+    _log(f"oracle_{h}x{w}", logit_err_rel=float(np.abs(logits - logit_ref).max() / np.abs(logit_ref).max()),
+         flips=float(((logits > 0) != (logit_ref > 0)).mean()))
     assert np.abs(logits - logit_ref).max() <= LOGIT_REL_TOL * np.abs(logit_ref).max()
     assert ((logits > 0) != (logit_ref > 0)).mean() <= MAX_FLIP
     assert (mask == (logits > 0)).all()
@@ -286,10 +313,13 @@ def test_full_size_batch_properties():
     wts = weights.random_weights(0, head_bias=-1.0)
     frames = synth.tiled_streams(16, 67, 45, 80, config_idx=1, n_unique=4)
     frames[8:] = frames[:8]                                         # chains 8..15 duplicate chains 0..7
-    p = BlobPipeline(80, 45, weights.to_blob(wts), 16, 67)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 16, 67, keep_logits=True, keep_stacked=True)
     blobs = p.process(frames)
     mask = p.read_mask()
     assert len(blobs) == 16 * 64
+    # oracle logits on 36 sampled windows: first / last / middle of a chain, both sides of every chain boundary
+    sample = sorted({0, 1, 31, 62, 63, 64, 65, 127, 128, 7 * 64 + 63, 8 * 64, 15 * 64, 15 * 64 + 63} | {int(k) for k in np.random.default_rng(0).integers(0, 1024, 23)})
+    _check_windows_against_oracle("c2_16x64", wts, p, frames, sample, 64)
     assert blobs == c_oracle.bboxcc_batch(mask, 1)
     assert blobs[: 8 * 64] == blobs[8 * 64:]
     assert (mask[: 8 * 64] == mask[8 * 64:]).all()
@@ -315,6 +345,10 @@ def test_config_c3_1080p_shard_properties():
     assert blobs[: 16 * 64] == blobs[16 * 64:]
     assert (p.read_stacked()[5 * 64: 6 * 64] == mpr.tensorise_stream(frames[5], 4, 1)).all()
     assert 0.005 < mask.mean() < 0.6
+    p2 = BlobPipeline(120, 68, weights.to_blob(wts), 32, 67, keep_stacked=True, keep_logits=True)
+    assert p2.process(frames) == blobs
+    sample = sorted({0, 63, 64, 15 * 64 + 63, 16 * 64, 31 * 64 + 63} | {int(k) for k in np.random.default_rng(1).integers(0, 2048, 26)})
+    _check_windows_against_oracle("c3_32x64", wts, p2, frames, sample, 64)
     assert p.process(frames) == blobs
 
 
@@ -337,6 +371,29 @@ def test_config_c4_4k_dense_worst_case(head_bias):
     scale = float(np.abs(ref).max())
     assert float(np.abs(logits[:2] - ref).max()) <= LOGIT_REL_TOL * scale
     assert float(((logits[:2] > 0) != (ref > 0)).mean()) <= MAX_FLIP
+
+
+def test_config_c5_bench_shape_128_chains_per_gpu():
+    """BASELINE configs[4] per GPU = the shape bench.py times (1024 concurrent 720p streams over 8 GPUs = 128 chains of 64
+    windows each, boxes returned in the sorttracker / cova wire format): boxes of all 8192 windows bit-exact for the device
+    mask (C oracle), oracle logits + masks on 40 sampled windows (chain ends, chain boundaries, the launch's last
+    tiles), every blob deserialises as the Vec<Bbox> sorttracker consumes."""
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.tiled_streams(128, 67, 45, 80, config_idx=1, n_unique=16)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 128, 67, keep_logits=True, keep_stacked=True, n_chunks=1)
+    blobs = p.process(frames)
+    assert len(blobs) == 8192
+    mask = p.read_mask()
+    assert blobs == c_oracle.bboxcc_batch(mask, 1)
+    for b in blobs[::257]:
+        for box in deserialize_vec(b):
+            assert box[4] == box[2] * box[3] and 0 <= box[0] < 80 and 0 <= box[1] < 45
+    sample = sorted({0, 1, 62, 63, 64, 127 * 64, 8191, 8190, 4095, 4096, 100 * 64 + 63, 101 * 64} |
+                    {int(k) for k in np.random.default_rng(2).integers(0, 8192, 28)})
+    _check_windows_against_oracle("c5_128x64", wts, p, frames, sample, 64)
+    # the streaming entry points (what bench.py's e2e leg calls) return the same bytes
+    p.submit(frames); p.submit(frames)
+    assert p.collect() == blobs and p.collect() == blobs
 
 
 def test_chunked_overlapped_processing_matches_single_chunk():
