@@ -48,10 +48,34 @@ __device__ __forceinline__ int uf_find(volatile int *parent, int i) {
     return i;
 }
 
+// Find with path compression.  parent[] only ever DECREASES and always names a block of the same (eventual) component:
+// links go from a root to a smaller index, and a compression replaces a parent by one of its ancestors.  Lowering
+// parent[j] with atomicMin to a root found a moment ago is therefore safe whatever other threads do meanwhile (the value
+// may be a stale root, it is still an ancestor), no cycle can form (parent[j] < j for every non-root), and every access
+// to parent[] stays an atomic or a volatile load.  Without it a dense mask builds one link per block row (the run heads
+// of consecutive rows chain up), and every find of a block in row r walks r links: 41 % of the kernel's stall samples at
+// 4K sat in this loop (profiles/r2c_ccl_lines.txt).
+__device__ __forceinline__ int uf_find_compress(int *parent, int i) {
+    volatile int *vp = parent;
+    int r = vp[i];
+    if (r == i) return i;
+    int p, hops = 0;
+    while ((p = vp[r]) != r) { r = p; hops++; }
+    if (hops) {
+        // second walk: everything on the path now points at r
+        int j = i;
+        while ((p = vp[j]) > r) {
+            atomicMin(&parent[j], r);
+            j = p;
+        }
+    }
+    return r;
+}
+
 __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_compress(parent, a);
+        b = uf_find_compress(parent, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
         int old = atomicMin(&parent[a], b);   // link the larger root under the smaller one
@@ -133,12 +157,27 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         const int by = run_by, bx = run_bx;
         COVA_CCL_ADVANCE(run_by, run_bx);
         if (!c) continue;
-        if (lane == 0 && bx > 0 && (c & 0x5) && (code[b - 1] & 0xA)) uf_union(parent, b, b - 1);
+        const int cw = bx > 0 ? code[b - 1] : 0;
+        const bool west_b = (c & 0x5) && (cw & 0xA);                                           // b-1 ~ b along the row
+        if (lane == 0 && west_b) uf_union(parent, b, b - 1);
         if (by > 0) {
-            int u = b - A.nbx;
-            if ((c & 0x3) && (code[u] & 0xC)) uf_union(parent, b, u);                          // north: my top row / its bottom row
-            if (bx > 0 && (c & 0x1) && (code[u - 1] & 0x8)) uf_union(parent, b, u - 1);        // north-west corner
-            if (bx + 1 < A.nbx && (c & 0x2) && (code[u + 1] & 0x4)) uf_union(parent, b, u + 1);  // north-east corner
+            const int u = b - A.nbx;
+            const int cu = code[u];
+            const int cuw = bx > 0 ? code[u - 1] : 0, cue = bx + 1 < A.nbx ? code[u + 1] : 0;
+            const bool n = (c & 0x3) && (cu & 0xC);                                            // north: my top row / its bottom row
+            const bool west_u = (cu & 0x5) && (cuw & 0xA), west_ue = (cue & 0x5) && (cu & 0xA);   // u-1 ~ u, u ~ u+1
+            const bool n_w = west_b && (cw & 0x3) && (cuw & 0xC);                              // b ~ b-1 and b-1 has its own north link
+            // Links that other links imply are skipped (every union costs two finds).  All links of the phase are in place
+            // at its closing barrier, so transitivity may lean on links other threads make:
+            //   north:      b ~ b-1 ~ u-1 ~ u   when the west neighbour has a north link and the two north blocks are joined
+            //               - on a dense mask only the first block of every run-to-run contact is left;
+            //   north-west: b ~ u ~ u-1, or b ~ b-1 ~ u-1;     north-east: b ~ u ~ u+1
+            const bool do_n = n && !(n_w && west_u);
+            const bool nw = (c & 0x1) && (cuw & 0x8) && !(n && west_u) && !n_w;
+            const bool ne = (c & 0x2) && (cue & 0x4) && !(n && west_ue);
+            if (do_n) uf_union(parent, b, u);
+            if (nw) uf_union(parent, b, u - 1);
+            if (ne) uf_union(parent, b, u + 1);
         }
     }
     __syncthreads();

@@ -18,14 +18,20 @@ def time_ccl(p, masks, reps=5):
     boxes = p.fetch_boxes_raw()[2]
     return float(np.median(ts[1:])), float(((boxes.astype(np.int64) - 8) // 24).mean())
 
-for (h, w, n_streams) in ((45, 80, 128), (135, 240, 16)):
+CASES = ((45, 80, 128, -1.0), (68, 120, 64, -1.0), (135, 240, 16, -1.0), (135, 240, 16, 0.0))
+if os.environ.get("CASES"):             # e.g. CASES=3 -> only the dense 4K case
+    CASES = tuple(CASES[int(i)] for i in os.environ["CASES"].split(","))
+for (h, w, n_streams, hb) in CASES:
     fps = 67
-    p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=1)
+    p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=hb)), n_streams, fps, n_chunks=1)
     n = p.windows_for(n_streams, fps)
     p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1)); p.run(); p.sync()
     m = p.read_mask()
     ms, nb = time_ccl(p, m)
-    print(f"{h}x{w} blobnet masks      n={n} {ms*1e3:8.1f} us  {n/ms/1e3:8.2f} M masks/s  boxes/frame {nb:.1f}  fg {m.mean():.3f}")
+    if os.environ.get("ONLY_NET"):
+        print(f"{h}x{w} blobnet masks hb={hb} n={n} {ms*1e3:8.1f} us  {n/ms/1e3:8.2f} M masks/s  boxes/frame {nb:.1f}  fg {m.mean():.3f}")
+        continue
+    print(f"{h}x{w} blobnet masks hb={hb} n={n} {ms*1e3:8.1f} us  {n/ms/1e3:8.2f} M masks/s  boxes/frame {nb:.1f}  fg {m.mean():.3f}")
     for name, pat in synth.mask_patterns(h, w, seed=1).items():
         mm = np.broadcast_to(pat, (n,) + pat.shape).copy()
         ms, nb = time_ccl(p, mm)

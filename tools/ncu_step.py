@@ -9,7 +9,7 @@ from cova_b200.elements import BlobPipeline
 n_streams, fps = int(os.environ.get("STREAMS", 128)), 67
 h, w = int(os.environ.get("H", 45)), int(os.environ.get("W", 80))
 steps = int(os.environ.get("STEPS", 4))
-p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=-1.0)), n_streams, fps, n_chunks=int(os.environ.get("CHUNKS", 1)))
+p = BlobPipeline(w, h, weights.to_blob(weights.random_weights(0, head_bias=float(os.environ.get("HEAD_BIAS", -1.0)))), n_streams, fps, n_chunks=int(os.environ.get("CHUNKS", 1)))
 p.load_frames(synth.tiled_streams(n_streams, fps, h, w, 1))
 if os.environ.get("DBG"):
     p.set_debug(int(os.environ["DBG"]))       # cova_pipeline_set_debug flags (experiments)
