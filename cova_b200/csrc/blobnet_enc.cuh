@@ -461,7 +461,7 @@ inline bool try_launch_e(LayerParams p, int n_sms, cudaStream_t st, cudaError_t 
         if (plan_smem_e<C>(p.Ls, p.n_stage).total <= (uint32_t)tc::kSmemLimit) break;
     if (p.n_stage < min_stage) return false;
     const SmemPlanE sp = plan_smem_e<C>(p.Ls, p.n_stage);
-    err = cudaFuncSetAttribute(enc_ws_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    err = cudaFuncSetAttribute(enc_ws_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);   // see tc::try_launch
     if (err != cudaSuccess) return true;
     ELayerExtra ex;
     ex.divS = make_fastdiv((uint32_t)p.gin.S);

@@ -302,7 +302,7 @@ inline bool try_launch_enc1(LayerParams p, Enc1Extra ex, int n_sms, cudaStream_t
     if (p.n_stage < 2) return false;
     // more than half of the SM's shared memory: one CTA per SM (the CTA allocates all 512 TMEM columns)
     const uint32_t total = std::max<uint32_t>(plan_smem1(p.Ls, p.n_stage, p.w_bytes).total, 120u * 1024u);
-    err = cudaFuncSetAttribute(enc1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    err = cudaFuncSetAttribute(enc1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);   // see tc::try_launch
     if (err != cudaSuccess) return true;
     err = launch_pdl(enc1_fused_kernel, dim3((unsigned)ctas), dim3(kThreads1), total, st, !(p.dbg & kDbgNoPdl), p, ex);
     return true;

@@ -761,7 +761,11 @@ inline bool try_launch(LayerParams p, int n_sms, cudaStream_t st, cudaError_t &e
         if (plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>()).total <= (uint32_t)kSmemLimit) break;
     if (p.n_stage < min_stage) return false;
     const SmemPlan sp = plan_smem<C>(p.Ls, p.n_stage, p.w_bytes, epi_floats<C>());
-    err = cudaFuncSetAttribute(shiftgemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total);
+    // The attribute belongs to the FUNCTION (per device), not to a launch, and the last write wins: two handles with
+    // different grids on two threads would otherwise lower it under each other's feet between "set" and "launch"
+    // (seen as cudaErrorInvalidValue by tests/test_gpu_parity.py::test_two_threads_two_handles...).  Always the same value,
+    // the architectural maximum, makes the call idempotent; occupancy follows the size actually requested at launch.
+    err = cudaFuncSetAttribute(shiftgemm_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (err != cudaSuccess) return true;
     int ctas = n_sms / nsplit;
     if (ctas > p.n_groups) ctas = p.n_groups;

@@ -78,7 +78,12 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
         b = uf_find_compress(parent, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }
-        int old = atomicMin(&parent[a], b);   // link the larger root under the smaller one
+        // Link the larger ROOT under the smaller one - compare-and-swap, not atomicMin: an atomicMin on an `a` that has
+        // meanwhile been linked elsewhere would REPLACE that committed edge (the displaced pair is re-united by this
+        // thread's next iteration, but a concurrent compression that has already seen the new edge can short-cut across
+        // it before that happens, and the re-union then finds nothing left to do - one component too many, once in a few
+        // hundred dense masks).  With CAS an edge, once made, is only ever moved to one of its own ancestors.
+        int old = atomicCAS(&parent[a], a, b);
         if (old == a) return;
         a = old;
     }

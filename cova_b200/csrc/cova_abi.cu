@@ -239,11 +239,13 @@ struct CclBuffers {
     int threads = 0;
 };
 
+constexpr int kCclSmemLimit = tc::kSmemLimit - 1024;   // dynamic part: the kernel also has a few bytes of static shared memory
+
 static int ccl_alloc(CclBuffers &b, int H, int W, int max_masks, bool own_masks) {
     b.H = H; b.W = W; b.nbx = (W + 1) / 2; b.nby = (H + 1) / 2; b.nb = b.nbx * b.nby; b.max_masks = max_masks;
     b.threads = ccl_threads_for(b.nb);
     b.smem = ccl_smem_bytes(b.nb, b.threads);
-    if (b.smem > (size_t)tc::kSmemLimit || b.nb >= 0xFFFF)
+    if (b.smem > (size_t)kCclSmemLimit || b.nb >= 0xFFFF)
         return set_err(COVA_E_UNSUPPORTED, "mask grid too large for the shared-memory CCL kernel");
     b.blob_cap = (size_t)max_masks * (8 + 24 * (size_t)b.nb);
     if (own_masks) COVA_CUDA(cudaMalloc(&b.d_masks, (size_t)max_masks * H * W));
@@ -276,9 +278,10 @@ static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_
     a.div_nbx = make_fastdiv((uint32_t)std::max(2, b.nbx));
     a.step_by = b.threads / b.nbx; a.step_bx = b.threads % b.nbx;
     if (reset_cursor) COVA_CUDA(cudaMemsetAsync(b.d_cursor, 0, 2 * sizeof(unsigned long long), st));
-    // the attribute is per function AND per device, last write wins: handles of different grids (or on different devices)
-    // share ccl_bbox_kernel, so it is set for every launch like the tcgen05 kernels do (try_launch)
-    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem));
+    // the attribute is per function AND per device, last write wins: handles of different grids (or on different devices,
+    // or on different threads) share ccl_bbox_kernel, so it is set for every launch and always to the same value, the
+    // architectural maximum (see tc::try_launch)
+    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemLimit));
     COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, pdl, a));
     return COVA_OK;
 }

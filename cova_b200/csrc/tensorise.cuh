@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(256) tensorise_x0_kernel(const uint32_t *__res
 // fp16 of the clipped bytes without integer->float conversions: 0x6400 | n is the half 1024 + n for n < 1024, and
 // subtracting 1024 in half arithmetic is exact.  q = [mb_weight, |mv_x|, |mv_y|, stale]; returns (c0 c1 | c2 0) as two half2.
 __device__ __forceinline__ uint2 quad_to_half4(uint32_t q) {
-    const uint32_t m = __vminu4(q, 0x06060606u);                       // clip(., 0, 6) of a u8 = min(., 6), all four bytes at once
+    // clip(., 0, 6) of a u8 = min(., 6), all four bytes at once.  __vminu4 is emulated on sm_100 (a dozen instructions);
+    // SWAR: bit 7 of byte i of `ge` is set iff byte i >= 7 (low 7 bits + 121 carry into bit 7, or bit 7 already set)
+    const uint32_t ge = (((q & 0x7f7f7f7fu) + 0x79797979u) | q) & 0x80808080u;
+    const uint32_t sel = (ge >> 7) * 0xffu;                            // 0xff in every byte that is >= 7
+    const uint32_t m = (q & ~sel) | (0x06060606u & sel);
     const uint32_t lo = __byte_perm(m, 0u, 0x4140) | 0x64006400u;      // bytes 0, 1 into the low byte of each half
     const uint32_t hi = __byte_perm(m, 0u, 0x4442) | 0x64006400u;      // byte 2; the fourth channel stays 0 (byte 3 is dropped)
     const __half2 k = __half2half2(__ushort_as_half((unsigned short)0x6400));
