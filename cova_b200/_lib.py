@@ -12,7 +12,7 @@ SO_VAL_PATH = os.path.join(_HERE, "libcova_b200_val.so")   # product sources + t
 OK, DROPPED = 0, 1
 E_INVAL, E_CUDA, E_NOMEM, E_TOOSMALL, E_WEIGHTS, E_UNSUPPORTED, E_NODEVICE, E_NUMERIC, E_STATE = -1, -2, -3, -4, -5, -6, -7, -8, -9
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
-FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED = 0x100, 0x200
+FLAG_KEEP_LOGITS, FLAG_KEEP_STACKED, FLAG_INPUT_PACKED16 = 0x100, 0x200, 0x400
 SUBMIT_CONTINUE = 1
 
 
@@ -71,6 +71,9 @@ SIGNATURES = {
     "cova_pipeline_submit_host2": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp, _vp, ctypes.c_uint32]),
     "cova_pipeline_collect_host2": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _szp, _vp, _vp, _u32p, _vp, _vp]),
     "cova_pipeline_reset_streams": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32]),
+    "cova_packer_new": (ctypes.c_int, [_vpp, ctypes.c_uint32]),
+    "cova_packer_free": (None, [_vp]),
+    "cova_packer_pack": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t]),
     "cova_pipeline_load_masks": (ctypes.c_int, [_vp, _vp, ctypes.c_uint32, ctypes.c_int]),
     "cova_pipeline_read_stacked": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
     "cova_pipeline_read_mask": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),

@@ -388,7 +388,8 @@ struct cova_pipeline {
     uint32_t W = 0, H = 0, T = 0, gamma = 1, max_streams = 0, max_fps = 0, max_windows = 0, flags = 0, impl = 0;
     uint32_t cc_threshold = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    size_t frame_bytes = 0;
+    size_t frame_bytes = 0;              // bytes of one frame in the pool: 4 per macroblock, or 2 with COVA_FLAG_INPUT_PACKED16
+    bool packed = false;
     uint8_t *d_frames = nullptr;
     int *d_newest = nullptr;
     uint32_t cur_streams = 0, cur_fps = 0, cur_windows = 0, table_streams = 0, table_fps = 0, table_first = 0;
@@ -492,6 +493,11 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     if (gamma < 1 || !max_streams || max_fps < timestep) return set_err(COVA_E_INVAL, "need gamma >= 1, max_streams >= 1, max_frames_per_stream >= timestep");
     if (w_mb < 16 || h_mb < 16) return set_err(COVA_E_UNSUPPORTED, "macroblock grid must be at least 16x16 for four 2x poolings");
     if ((flags & 0xffu) > COVA_IMPL_SIMT) return set_err(COVA_E_INVAL, "unknown implementation selector");
+    if (flags & COVA_FLAG_INPUT_PACKED16) {
+        if (flags & COVA_FLAG_KEEP_STACKED) return set_err(COVA_E_INVAL, "the stacked RGBA windows cannot be rebuilt from packed input (byte 3 and values above 6 are gone)");
+        if ((flags & 0xffu) == COVA_IMPL_SIMT) return set_err(COVA_E_UNSUPPORTED, "the validation kernels read the 4-byte input format");
+        if (w_mb & 1) return set_err(COVA_E_UNSUPPORTED, "packed input needs an even macroblock-grid width");
+    }
 #ifndef COVA_VALIDATION
     if ((flags & 0xffu) == COVA_IMPL_SIMT)
         return set_err(COVA_E_UNSUPPORTED, "the validation kernels (COVA_IMPL_SIMT) are not part of this build; use libcova_b200_val.so");
@@ -560,7 +566,8 @@ extern "C" int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb,
     p->gp1 = make_geom(p->sizes_h[1], p->sizes_w[1], kEncCout[0], 1, F);
     if ((rc = alloc_zero(&p->x0f, p->gx0f))) return fail(rc);
     if ((rc = alloc_zero(&p->p1, p->gp1))) return fail(rc);
-    p->frame_bytes = (size_t)w_mb * h_mb * 4;
+    p->packed = (flags & COVA_FLAG_INPUT_PACKED16) != 0;
+    p->frame_bytes = (size_t)w_mb * h_mb * (p->packed ? 2 : 4);
     cudaError_t e = cudaMalloc(&p->slot[0].d_frames, p->frame_bytes * max_streams * max_fps);
     p->d_frames = p->slot[0].d_frames;
     if (e == cudaSuccess) e = cudaMalloc(&p->d_newest, sizeof(int) * std::max(1, N));
@@ -746,8 +753,8 @@ static int tensorise_chunk(cova_pipeline *p) {
         long long total = (long long)F * p->H * p->gx0f.Wh;
         int blocks = (int)std::min<long long>((total + 255) / 256, (long long)p->n_sms * 32);
         if (total >= (1ll << 32)) return set_err(COVA_E_UNSUPPORTED, "chunk too large for the frame tensorisation kernel (32-bit index)");
-        COVA_CUDA(launch_pdl(tensorise_frames_kernel, dim3((unsigned)blocks), dim3(256), 0, p->stream, !(p->dbg & kDbgNoPdl),
-                             reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F,
+        COVA_CUDA(launch_pdl(p->packed ? tensorise_frames_kernel<true> : tensorise_frames_kernel<false>, dim3((unsigned)blocks), dim3(256), 0,
+                             p->stream, !(p->dbg & kDbgNoPdl), reinterpret_cast<const uint32_t *>(frames), p->x0f, p->gx0f, F,
                              make_fastdiv((uint32_t)std::max(2, p->gx0f.Wh)), make_fastdiv((uint32_t)std::max<uint32_t>(2u, p->H))));
         p->launches++;
         prof_mark(p, "tensorise_frames");

@@ -6,6 +6,7 @@
 
 #include "../../include/cova_b200.h"
 #include "cova_select.hpp"
+#include "frame_packer.hpp"
 #include "gop_demux.hpp"
 #include "sort_tracker.hpp"
 
@@ -281,5 +282,29 @@ extern "C" int cova_demux_annexb_frames(const uint8_t *data, size_t len, cova_sa
 extern "C" int cova_gopsplit_ranges(const uint32_t *flags, size_t n_frames, uint32_t n_pads, uint64_t *first_frame, uint64_t *end_frame) {
     if ((!flags && n_frames) || !first_frame || !end_frame) return fail(COVA_E_INVAL, "null argument");
     if (!cova::host::gopsplit_ranges(flags, n_frames, n_pads, first_frame, end_frame)) return fail(COVA_E_INVAL, "there are no pads");
+    return COVA_OK;
+}
+
+// =================================================================================================
+// host packer for COVA_FLAG_INPUT_PACKED16 (frame_packer.hpp)
+// =================================================================================================
+struct cova_packer {
+    cova::host::Packer pk;
+    explicit cova_packer(unsigned n) : pk(n) {}
+};
+extern "C" int cova_packer_new(cova_packer **out, uint32_t n_threads) {
+    if (!out) return fail(COVA_E_INVAL, "null out");
+    *out = nullptr;
+    try {
+        *out = new cova_packer(n_threads);
+    } catch (const std::exception &) {      // bad_alloc, or std::system_error when a thread cannot be started
+        return fail(COVA_E_NOMEM, "could not start the packer's worker threads");
+    }
+    return COVA_OK;
+}
+extern "C" void cova_packer_free(cova_packer *pk) { delete pk; }
+extern "C" int cova_packer_pack(cova_packer *pk, const uint8_t *quads, uint16_t *out, size_t n_mb) {
+    if (!pk || (!quads && n_mb) || (!out && n_mb)) return fail(COVA_E_INVAL, "null argument");
+    pk->pk.pack(quads, out, n_mb);
     return COVA_OK;
 }

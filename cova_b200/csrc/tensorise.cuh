@@ -93,6 +93,12 @@ __device__ __forceinline__ uint2 quad_to_half4(uint32_t q) {
     return make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
 }
 
+// PACKED: the frames are in the 2-byte packed input format (include/cova_b200.h, COVA_FLAG_INPUT_PACKED16): one u16 per
+// macroblock, bits 0-2 mb_weight, 3-5 |mv_x|, 6-8 |mv_y|, each already clipped to 6 by the host packer - exact for BlobNet,
+// whose first operation is clip(., 0, 6) (utils/model/preprocessing.py:5-8), and half the host->device bytes.  W is even.
+__device__ __forceinline__ uint32_t unpack16(uint32_t p) { return (p & 7u) | ((p & 0x38u) << 5) | ((p & 0x1c0u) << 10); }
+
+template <bool PACKED>
 __global__ void __launch_bounds__(256) tensorise_frames_kernel(const uint32_t *__restrict__ frames, uint4 *__restrict__ x0f,
                                                                Geom g, int n_frames, FastDiv div_wh, FastDiv div_h) {
     pdl_launch_dependents();
@@ -114,7 +120,10 @@ __global__ void __launch_bounds__(256) tensorise_frames_kernel(const uint32_t *_
                 const uint32_t r = Wh > 1 ? fast_div(i, div_wh) : i, x2 = i - r * Wh;      // r = f * H + y
                 const uint32_t *src = frames + ((size_t)r * W + 2 * x2);
                 rr[k] = r; xx[k] = x2;
-                if (pair_aligned) {
+                if constexpr (PACKED) {
+                    const uint32_t pp = __ldg(frames + ((size_t)r * (W >> 1) + x2));     // one x pair = two u16
+                    q0[k] = unpack16(pp & 0xffffu); q1[k] = unpack16(pp >> 16);
+                } else if (pair_aligned) {
                     const uint2 q = __ldg(reinterpret_cast<const uint2 *>(src));
                     q0[k] = q.x; q1[k] = q.y;
                 } else {

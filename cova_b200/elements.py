@@ -61,6 +61,35 @@ class PinnedBuffer:
             pass
 
 
+class FramePacker:
+    """Host packer for BlobPipeline(packed_input=True): decoder quads [.., h, w, 4] u8 -> [.., h, w] u16
+    (cova_packer_pack: min(b, 6) of bytes 0-2 in 3 bits each; worker threads live as long as the packer)."""
+
+    def __init__(self, n_threads: int = 0):
+        self._h = ctypes.c_void_p()
+        check(_lib.load().cova_packer_new(ctypes.byref(self._h), n_threads))
+
+    def pack(self, quads: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        a = np.ascontiguousarray(quads, dtype=np.uint8)
+        assert a.shape[-1] == 4, a.shape
+        if out is None:
+            out = np.empty(a.shape[:-1], dtype=np.uint16)
+        assert out.dtype == np.uint16 and out.size == a.size // 4 and out.flags.c_contiguous
+        check(_lib.load().cova_packer_pack(self._h, _ptr(a), _ptr(out), out.size))
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.load().cova_packer_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MetaPreprocess:
     """`metapreprocess` element: one instance == one stream == one sliding window."""
 
@@ -337,13 +366,16 @@ class BlobPipeline:
     def __init__(self, w_mb: int, h_mb: int, weights_blob: bytes, max_streams: int, max_frames_per_stream: int,
                  timestep: int = 4, gamma: int = 1, cc_threshold: int = 1, device: int = 0,
                  impl: int = _lib.IMPL_TCGEN05, keep_logits: bool = False, keep_stacked: bool = False, n_chunks: int = 0,
-                 validation: bool = False):
+                 validation: bool = False, packed_input: bool = False):
         # validation=True (or impl=IMPL_SIMT) binds this handle to libcova_b200_val.so, the build that also holds the
         # fp32 validation kernels; the product library refuses IMPL_SIMT
         self._L = _lib.load_validation() if (validation or impl == _lib.IMPL_SIMT) else _lib.load()
         self._h = ctypes.c_void_p()
         flags = impl | (_lib.FLAG_KEEP_LOGITS if keep_logits else 0) | (_lib.FLAG_KEEP_STACKED if keep_stacked else 0)
         flags |= (n_chunks & 0xff) << 16
+        flags |= _lib.FLAG_INPUT_PACKED16 if packed_input else 0
+        # packed_input: every frames argument is [n_streams, frames, h_mb, w_mb] u16 (FramePacker) instead of [.., 4] u8
+        self.packed_input = packed_input
         self._wbuf = ctypes.create_string_buffer(weights_blob, len(weights_blob))
         self._check(self._L.cova_pipeline_new(ctypes.byref(self._h), device, w_mb, h_mb, timestep, gamma, max_streams,
                                             max_frames_per_stream, ctypes.cast(self._wbuf, ctypes.c_void_p),
@@ -370,13 +402,22 @@ class BlobPipeline:
         self._check(self._L.cova_pipeline_n_windows(self._h, n_streams, frames_per_stream, ctypes.byref(n)))
         return n.value
 
+    def _frames(self, frames) -> np.ndarray:
+        if self.packed_input:
+            a = np.ascontiguousarray(frames, dtype=np.uint16)
+            assert a.shape[2:] == (self.h_mb, self.w_mb), a.shape
+        else:
+            a = np.ascontiguousarray(frames, dtype=np.uint8)
+            assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
+        return a
+
     # ---- stages
     def load_frames(self, frames, n_streams: int | None = None, frames_per_stream: int | None = None):
-        """frames: numpy u8 array (host) or an int device pointer (then the two counts are required)."""
+        """frames: numpy array (host; u8 quads, or u16 with packed_input) or an int device pointer (then the two counts
+        are required)."""
         if isinstance(frames, np.ndarray):
-            a = np.ascontiguousarray(frames, dtype=np.uint8)
+            a = self._frames(frames)
             n_streams, frames_per_stream = a.shape[0], a.shape[1]
-            assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
             self._keep = a
             self._check(self._L.cova_pipeline_load_frames(self._h, _ptr(a), n_streams, frames_per_stream, 0))
         else:
@@ -441,8 +482,7 @@ class BlobPipeline:
         stream_ids[s] (default 0, 1, ...), `pts[s, f]` is echoed per window by collect(meta=True), and cont=True continues
         the streams from their previous batch (carried timestep-1 frames + gamma phase) like one long-lived metapreprocess
         element would."""
-        a = np.ascontiguousarray(frames, dtype=np.uint8)
-        assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
+        a = self._frames(frames)
         if stream_ids is None and pts is None and cont is None:
             self._ensure_out(blob_cap or self._worst_case_cap(self.windows_for(a.shape[0], a.shape[1])))
             self._check(self._L.cova_pipeline_submit_host(self._h, _ptr(a), a.shape[0], a.shape[1]))
@@ -493,9 +533,8 @@ class BlobPipeline:
     def process(self, frames: np.ndarray, raw: bool = False, blob_cap: int | None = None):
         """Host frames -> per-window bincode(Vec<Bbox>) blobs (stream-major, time-minor): a list of bytes,
         or with raw=True the (blob, offsets, lens) arrays without per-window Python objects."""
-        a = np.ascontiguousarray(frames, dtype=np.uint8)
+        a = self._frames(frames)
         n_streams, fps = a.shape[0], a.shape[1]
-        assert a.shape[2:] == (self.h_mb, self.w_mb, 4), a.shape
         n = self.windows_for(n_streams, fps)
         self._ensure_out(blob_cap or self._worst_case_cap(n))
         self._collect_idx = 0

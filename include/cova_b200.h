@@ -112,6 +112,13 @@ typedef struct cova_pipeline cova_pipeline;
 #define COVA_IMPL_SIMT 1u    /* validation kernels (CUDA cores, fp32 weights) used by the tests */
 #define COVA_FLAG_KEEP_LOGITS 0x100u  /* also store fp32 logits (parity tests) */
 #define COVA_FLAG_KEEP_STACKED 0x200u /* also materialise the stacked RGBA windows (parity tests) */
+/* Frames arrive in the 2-byte packed format instead of the decoder's 4-byte quads: one little-endian u16 per macroblock,
+ * bits 0-2 min(mb_weight, 6), bits 3-5 min(|mv_x|, 6), bits 6-8 min(|mv_y|, 6), the rest 0 (cova_packer_pack produces it).
+ * Exact for BlobNet - its first operation is clip(x, 0, 6) (utils/model/preprocessing.py:5-8) and byte 3 never reaches it
+ * (nvinfer drops the alpha channel, config/blobnet/amsterdam_b128.txt:7,9) - and half the host->device bytes of a path
+ * whose end-to-end rate is bound by exactly those.  Every frames argument of such a pipeline is
+ * [n_streams][frames][h_mb][w_mb] u16.  Not combinable with COVA_FLAG_KEEP_STACKED; w_mb must be even. */
+#define COVA_FLAG_INPUT_PACKED16 0x400u
 #define COVA_FLAG_CHUNKS(n) (((uint32_t)(n) & 0xffu) << 16) /* process a batch in n chunks of whole chains (0 = auto) */
 
 int cova_pipeline_new(cova_pipeline **out, int device, uint32_t w_mb, uint32_t h_mb, uint32_t timestep,
@@ -176,6 +183,14 @@ int cova_pipeline_collect_host2(cova_pipeline *p, uint8_t *blob, size_t blob_cap
                                 uint64_t *lens, uint32_t *n_windows, uint32_t *win_stream_ids, uint64_t *win_pts);
 /* forget the state of the given streams (NULL = all): their next CONTINUED batch starts with an empty window */
 int cova_pipeline_reset_streams(cova_pipeline *p, const uint32_t *stream_ids, uint32_t n);
+
+/* Host-side packer for COVA_FLAG_INPUT_PACKED16: n_mb macroblock quads (the decoder's [mb_weight, |mv_x|, |mv_y|, stale]
+ * bytes, h264_mb.c:822-855) -> n_mb u16.  A packer owns n_threads worker threads (0 = one per online CPU, at most 64);
+ * pack() splits the range evenly over them and returns when all are done.  AVX2 when the CPU has it.  Host C++, no CUDA. */
+typedef struct cova_packer cova_packer;
+int cova_packer_new(cova_packer **out, uint32_t n_threads);
+void cova_packer_free(cova_packer *pk);
+int cova_packer_pack(cova_packer *pk, const uint8_t *quads, uint16_t *out, size_t n_mb);
 
 /* feed a mask batch straight to the CCL stage (u8 [n][h_mb][w_mb]; is_device as above) */
 int cova_pipeline_load_masks(cova_pipeline *p, const uint8_t *masks, uint32_t n, int is_device);

@@ -593,3 +593,39 @@ def test_ccl_dense_mask_stress(h, w, n):
         got = p.fetch_boxes()
         bad = [i for i in range(n) if got[i] != want[i]]
         assert not bad, (len(bad), bad[:5], float(dens[bad[0]]))
+
+
+# ----------------------------------------------------------------------------------------- packed input (2 bytes per macroblock)
+@pytest.mark.parametrize("h,w,gamma", [(45, 80, 1), (68, 120, 2), (34, 22, 1)])
+def test_packed_input_gives_bit_identical_results(h, w, gamma):
+    """COVA_FLAG_INPUT_PACKED16: the host packer keeps min(byte, 6) of bytes 0..2 - everything BlobNet can see after its
+    clip(x, 0, 6) - so logits, masks and boxes must be BIT-identical to the 4-byte path, through process(), the
+    streaming calls and continued streams."""
+    from cova_b200.elements import FramePacker
+    wts = weights.random_weights(3, head_bias=-1.0)
+    frames = synth.synth_streams(3, 13, h, w, config_idx=31)
+    frames[0, :, :, :, :3] = np.random.default_rng(0).integers(0, 256, frames[0, :, :, :, :3].shape, dtype=np.uint8)   # values far above 6
+    packed = FramePacker(4).pack(frames)
+    assert packed.dtype == np.uint16 and packed.shape == frames.shape[:-1] and int(packed.max()) < 512
+    a = BlobPipeline(w, h, weights.to_blob(wts), 3, 13, gamma=gamma, keep_logits=True)
+    b = BlobPipeline(w, h, weights.to_blob(wts), 3, 13, gamma=gamma, keep_logits=True, packed_input=True)
+    ra, rb = a.process(frames), b.process(packed)
+    assert ra == rb and len(ra) == a.n_windows > 0
+    assert (a.read_logits() == b.read_logits()).all() and (a.read_mask() == b.read_mask()).all()
+    assert (a.read_activation(0) == b.read_activation(0)).all()
+    b.submit(packed); b.submit(packed)
+    assert b.collect() == ra and b.collect() == ra
+    # continued stream: 6 + 7 frames
+    b.submit(packed[:, :6], stream_ids=[0, 1, 2]); first = b.collect()
+    b.submit(packed[:, 6:], stream_ids=[0, 1, 2], cont=True); second = b.collect()
+    wa, w1, w2 = len(ra) // 3, len(first) // 3, len(second) // 3
+    for s in range(3):
+        assert first[s * w1: (s + 1) * w1] + second[s * w2: (s + 1) * w2] == ra[s * wa: (s + 1) * wa]
+    with pytest.raises(_lib.CovaError):
+        BlobPipeline(w, h, weights.to_blob(wts), 1, 8, keep_stacked=True, packed_input=True)
+
+
+def test_packed_input_needs_an_even_width():
+    with pytest.raises(_lib.CovaError) as e:
+        BlobPipeline(37, 21, weights.to_blob(weights.random_weights(0)), 1, 8, packed_input=True)
+    assert e.value.code == _lib.E_UNSUPPORTED

@@ -122,3 +122,21 @@ def test_stream_batch_argument_validation():
     n = ctypes.c_size_t()
     assert lib.cova_pipeline_collect_host2(None, None, 0, ctypes.byref(n), None, None, None, None, None) == _lib.E_INVAL
     assert lib.cova_pipeline_reset_streams(None, None, 0) == _lib.E_INVAL
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_frame_packer_is_exact(threads):
+    """cova_packer_pack (AVX2 or scalar, any thread count) == min(b, 6) of bytes 0..2 in 3 bits each; byte 3 ignored;
+    odd lengths and lengths below the threading threshold included."""
+    from cova_b200.elements import FramePacker
+    rng = np.random.default_rng(threads)
+    pk = FramePacker(threads)
+    for n in (0, 1, 15, 16, 17, 3600, 65535, 65536, 128 * 3600 + 7):
+        q = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+        q[: n // 2, :3] = rng.integers(0, 8, (n // 2, 3), dtype=np.uint8)        # the realistic range, with 7 in it
+        want = (np.minimum(q[:, 0], 6).astype(np.uint16) | (np.minimum(q[:, 1], 6).astype(np.uint16) << 3)
+                | (np.minimum(q[:, 2], 6).astype(np.uint16) << 6))
+        got = pk.pack(q.reshape(n, 1, 4)).reshape(-1) if n else pk.pack(q.reshape(0, 1, 4)).reshape(-1)
+        assert (got == want).all(), n
+    fr = synth.synth_streams(2, 5, 45, 80, config_idx=1)
+    assert pk.pack(fr).shape == fr.shape[:-1]
