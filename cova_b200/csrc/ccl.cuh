@@ -14,6 +14,8 @@
 // O(run length) chains: all-ones 720p masks 2.58 ms -> 0.65 ms per 8192 masks, diagonal checkerboard 1.72 -> 0.43 ms
 // (tools/ccl_timing.py, B200).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cova {
@@ -37,67 +39,161 @@ struct CclArgs {
 // (by, bx) of block b + blockDim.x from those of block b
 #define COVA_CCL_ADVANCE(by, bx) do { bx += A.step_bx; by += A.step_by; if (bx >= A.nbx) { bx -= A.nbx; by++; } } while (0)
 
-__host__ __device__ inline size_t ccl_smem_bytes(int nb, int threads) {
-    // parent + 5 stat arrays (int) + codes (u8, padded) + warp scan scratch
-    return (size_t)nb * 6 * sizeof(int) + (size_t)((nb + 15) / 16) * 16 + (size_t)(threads / 32 + 4) * sizeof(int);
+// Shared-memory layouts.  WIDE: parent (i32) + per-block statistics [min x, min y, max x, max y, area] (i32 each) +
+// block code (u8) = 25 bytes per 2x2 block.  At 4K (8160 blocks) that is 204 KB, i.e. one CTA per SM for a kernel that
+// waits on shared-memory pointer chases, not on bandwidth.  COMPACT: parent u16 (block indices are below 65535), min x |
+// min y and max x | max y as 16-bit pairs in one word each, area u16 (at most 4 pixels per block) = 13 bytes per block:
+// 106 KB at 4K, two CTAs (64 warps) per SM.  16-bit parents are updated with compare-and-swap loops, the packed
+// statistics with a CAS that is skipped when the box would not grow (on a large component almost every update is a
+// no-op).  The wide layout keeps the native 32-bit atomics; the host picks COMPACT when the wide one would not leave room
+// for a second CTA.
+__host__ __device__ inline size_t ccl_smem_bytes(int nb, int threads, bool compact) {
+    const size_t per_block = compact ? (size_t)((nb + 1) / 2 * 2) * 2 * 2 + (size_t)nb * 8    // parent u16 + area u16 (even count), mn + mx u32
+                                     : (size_t)nb * 6 * sizeof(int);
+    // + block codes (u8) + the per-warp lists of foreground blocks (u16, ceil(nb / threads) * threads entries) + scan scratch
+    const size_t list = (size_t)((nb + threads - 1) / threads) * threads * 2;
+    return per_block + (size_t)((nb + 15) / 16) * 16 + (list + 15) / 16 * 16 + (size_t)(threads / 32 + 4) * sizeof(int);
 }
 
-__device__ __forceinline__ int uf_find(volatile int *parent, int i) {
-    int p;
-    while ((p = parent[i]) != i) i = p;
-    return i;
-}
+template <bool COMPACT>
+struct CclMem {
+    using PT = typename std::conditional<COMPACT, unsigned short, int>::type;
+    static constexpr int kNone = COMPACT ? 0xFFFF : -1;          // parent of a background block (never equals a block index)
+    PT *parent;
+    int *stat;                 // WIDE: [block][5]
+    uint32_t *mn, *mx;         // COMPACT: min x | min y << 16, max x | max y << 16
+    unsigned short *area;      // COMPACT
+    uint8_t *code;
+    unsigned short *list;      // per-warp lists of foreground blocks (bit 15: the block was lane 0 of its 32-block segment)
+    int *scan;
 
-// Find with path compression.  parent[] only ever DECREASES and always names a block of the same (eventual) component:
-// links go from a root to a smaller index, and a compression replaces a parent by one of its ancestors.  Lowering
-// parent[j] with atomicMin to a root found a moment ago is therefore safe whatever other threads do meanwhile (the value
-// may be a stale root, it is still an ancestor), no cycle can form (parent[j] < j for every non-root), and every access
-// to parent[] stays an atomic or a volatile load.  Without it a dense mask builds one link per block row (the run heads
-// of consecutive rows chain up), and every find of a block in row r walks r links: 41 % of the kernel's stall samples at
-// 4K sat in this loop (profiles/r2c_ccl_lines.txt).
-__device__ __forceinline__ int uf_find_compress(int *parent, int i) {
-    volatile int *vp = parent;
-    int r = vp[i];
-    if (r == i) return i;
-    int p, hops = 0;
-    while ((p = vp[r]) != r) { r = p; hops++; }
-    if (hops) {
-        // second walk: everything on the path now points at r
-        int j = i;
-        while ((p = vp[j]) > r) {
+    __device__ __forceinline__ CclMem(unsigned char *base, int nb, int nt) {
+        if constexpr (COMPACT) {
+            const int nbe = (nb + 1) / 2 * 2;
+            parent = reinterpret_cast<PT *>(base);
+            area = reinterpret_cast<unsigned short *>(base) + nbe;
+            mn = reinterpret_cast<uint32_t *>(area + nbe);
+            mx = mn + nb;
+            code = reinterpret_cast<uint8_t *>(mx + nb);
+            stat = nullptr;
+        } else {
+            parent = reinterpret_cast<PT *>(base);
+            stat = reinterpret_cast<int *>(base) + nb;
+            code = reinterpret_cast<uint8_t *>(stat + 5 * nb);
+            mn = mx = nullptr; area = nullptr;
+        }
+        list = reinterpret_cast<unsigned short *>(code + ((nb + 15) / 16) * 16);
+        scan = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(list) + ((size_t)((nb + nt - 1) / nt) * nt * 2 + 15) / 16 * 16);
+    }
+    // ---- parent[]: every concurrent access is an atomic or a volatile load
+    __device__ __forceinline__ int load(int i) const { return (int)reinterpret_cast<volatile PT *>(parent)[i]; }
+    __device__ __forceinline__ void lower(int j, int r) const {            // parent[j] = min(parent[j], r)
+        if constexpr (COMPACT) {
+            unsigned short cur = reinterpret_cast<volatile PT *>(parent)[j];
+            while ((int)cur > r) {
+                const unsigned short old = atomicCAS(&parent[j], cur, (unsigned short)r);
+                if (old == cur) break;
+                cur = old;
+            }
+        } else {
             atomicMin(&parent[j], r);
-            j = p;
         }
     }
-    return r;
-}
-
-__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
-    while (true) {
-        a = uf_find_compress(parent, a);
-        b = uf_find_compress(parent, b);
-        if (a == b) return;
-        if (a < b) { int t = a; a = b; b = t; }
-        // Link the larger ROOT under the smaller one - compare-and-swap, not atomicMin: an atomicMin on an `a` that has
-        // meanwhile been linked elsewhere would REPLACE that committed edge (the displaced pair is re-united by this
-        // thread's next iteration, but a concurrent compression that has already seen the new edge can short-cut across
-        // it before that happens, and the re-union then finds nothing left to do - one component too many, once in a few
-        // hundred dense masks).  With CAS an edge, once made, is only ever moved to one of its own ancestors.
-        int old = atomicCAS(&parent[a], a, b);
-        if (old == a) return;
-        a = old;
+    __device__ __forceinline__ int cas(int a, int b) const {                // link root a under b if a is still a root
+        if constexpr (COMPACT) return (int)atomicCAS(&parent[a], (unsigned short)a, (unsigned short)b);
+        else return atomicCAS(&parent[a], a, b);
     }
-}
+    __device__ __forceinline__ int find(int i) const {
+        int p;
+        while ((p = load(i)) != i) i = p;
+        return i;
+    }
+    // Find with path compression.  parent[] only ever DECREASES and always names a block of the same (eventual) component:
+    // links go from a ROOT to a smaller index (compare-and-swap: an edge, once made, is never replaced by another edge), and a
+    // compression moves a parent to one of its own ancestors.  All ancestors a block ever has lie on one chain, ordered by
+    // index, so "the smaller of the current parent and a root seen a moment ago" is always a valid ancestor whatever other
+    // threads do meanwhile, no cycle can form (parent[j] < j for every non-root).  Without compression a dense mask builds
+    // one link per block row (the run heads of consecutive rows chain up) and every find of a block in row r walks r links:
+    // 41 % of the kernel's stall samples at 4K sat in that loop (profiles/r2c_ccl_lines.txt).
+    __device__ __forceinline__ int find_compress(int i) const {
+        int r = load(i);
+        if (r == i) return i;
+        int p, hops = 0;
+        while ((p = load(r)) != r) { r = p; hops++; }
+        if (hops) {
+            int j = i;                                   // second walk: everything on the path now points at r
+            while ((p = load(j)) > r) {
+                lower(j, r);
+                j = p;
+            }
+        }
+        return r;
+    }
+    __device__ __forceinline__ void unite(int a, int b) const {
+        while (true) {
+            a = find_compress(a);
+            b = find_compress(b);
+            if (a == b) return;
+            if (a < b) { int t = a; a = b; b = t; }
+            // Link the larger ROOT under the smaller one - compare-and-swap, not atomicMin: an atomicMin on an `a` that has
+            // meanwhile been linked elsewhere would REPLACE that committed edge (the displaced pair is re-united by this
+            // thread's next iteration, but a concurrent compression that has already seen the new edge can short-cut across
+            // it before that happens, and the re-union then finds nothing left to do - one component too many, once in a few
+            // hundred dense masks).
+            const int old = cas(a, b);
+            if (old == a) return;
+            a = old;
+        }
+    }
+    // ---- statistics (live at roots; only foreground blocks can be roots)
+    __device__ __forceinline__ void stat_init(int b) const {
+        if constexpr (COMPACT) { mn[b] = 0xFFFFFFFFu; mx[b] = 0u; area[b] = 0; }
+        else { int *sb = stat + 5 * b; sb[0] = 0x7fffffff; sb[1] = 0x7fffffff; sb[2] = -1; sb[3] = -1; sb[4] = 0; }
+    }
+    __device__ __forceinline__ void stat_add(int r, int x0, int y0, int x1, int y1, int cnt) const {
+        if constexpr (COMPACT) {
+            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&mn[r]);
+            while (true) {
+                const uint32_t want = min(cur & 0xFFFFu, (uint32_t)x0) | (min(cur >> 16, (uint32_t)y0) << 16);
+                if (want == cur) break;                                  // the box already covers this block
+                const uint32_t old = atomicCAS(&mn[r], cur, want);
+                if (old == cur) break;
+                cur = old;
+            }
+            cur = *reinterpret_cast<volatile uint32_t *>(&mx[r]);
+            while (true) {
+                const uint32_t want = max(cur & 0xFFFFu, (uint32_t)x1) | (max(cur >> 16, (uint32_t)y1) << 16);
+                if (want == cur) break;
+                const uint32_t old = atomicCAS(&mx[r], cur, want);
+                if (old == cur) break;
+                cur = old;
+            }
+            // two u16 areas per word; a component has at most 4 * nb < 65536 pixels, so a half never carries into its neighbour
+            atomicAdd(reinterpret_cast<unsigned int *>(area) + (r >> 1), (unsigned int)cnt << (16 * (r & 1)));
+        } else {
+            int *sr = stat + 5 * r;
+            atomicMin(&sr[0], x0); atomicMax(&sr[2], x1);
+            atomicMin(&sr[1], y0); atomicMax(&sr[3], y1);
+            atomicAdd(&sr[4], cnt);
+        }
+    }
+    __device__ __forceinline__ int stat_area(int b) const { return COMPACT ? (int)area[b] : stat[5 * b + 4]; }
+    __device__ __forceinline__ void stat_get(int b, int &x0, int &y0, int &x1, int &y1) const {
+        if constexpr (COMPACT) { x0 = (int)(mn[b] & 0xFFFFu); y0 = (int)(mn[b] >> 16); x1 = (int)(mx[b] & 0xFFFFu); y1 = (int)(mx[b] >> 16); }
+        else { const int *sb = stat + 5 * b; x0 = sb[0]; y0 = sb[1]; x1 = sb[2]; y1 = sb[3]; }
+    }
+    // the area slot of a root becomes the root -> label map once the boxes are out
+    __device__ __forceinline__ void set_label(int b, int label) const { if constexpr (COMPACT) area[b] = (unsigned short)label; else stat[5 * b + 4] = label; }
+    __device__ __forceinline__ int label(int b) const { return COMPACT ? (int)area[b] : stat[5 * b + 4]; }
+};
 
+template <bool COMPACT>
 __global__ void ccl_bbox_kernel(CclArgs A) {
     extern __shared__ __align__(16) unsigned char ccl_smem[];
     const int nb = A.nbx * A.nby;
-    int *parent = reinterpret_cast<int *>(ccl_smem);
-    // per-block statistics interleaved, [block][min x, min y, max x, max y, area]: one base address per block (stride of 5
-    // words = conflict-free across a warp) instead of five array bases
-    int *stat = parent + nb;
-    uint8_t *code = reinterpret_cast<uint8_t *>(stat + 5 * nb);
-    int *scan = reinterpret_cast<int *>(code + ((nb + 15) / 16) * 16);
+    const CclMem<COMPACT> M(ccl_smem, nb, (int)blockDim.x);
+    uint8_t *code = M.code;
+    int *scan = M.scan;
     __shared__ unsigned long long s_off;
 
     const int frame = blockIdx.x;
@@ -115,6 +211,14 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     const int by_first = A.nbx > 1 ? (int)fast_div((uint32_t)tid, A.div_nbx) : tid;
     const int bx_first = tid - by_first * A.nbx;
     const bool w_even = (A.W & 1) == 0;          // then every 2x2 block row is one aligned 16-bit load
+    // Foreground blocks are also appended to a list private to the warp (ballot + popcount, no cross-warp scan): the merge
+    // and statistics passes below then run over lists of foreground blocks only, with full warps - on the masks the network
+    // produces three blocks in four are background, and a warp that carries one foreground lane through a find loop pays
+    // for 32.  A warp owns the 32-block segments base + 32*wid .. of every pass over the grid, i.e. a fine interleave of the
+    // whole mask, so the lists are balanced.
+    const int iters = (nb + nt - 1) / nt;
+    unsigned short *my_list = M.list + (size_t)(tid >> 5) * iters * 32;
+    int n_fg = 0;                                    // warp-uniform: entries in my_list
     int run_by = by_first, run_bx = bx_first;
     for (int base = 0; base < nb; base += nt) {
         const int b = base + tid;
@@ -145,26 +249,24 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         if (b < nb) {
             const int start_lane = 31 - __clz((int)(starts & (0xffffffffu >> (31 - lane))));
             code[b] = (uint8_t)c;
-            parent[b] = c ? b - lane + start_lane : -1;
-            if (c) {                                     // statistics live at roots, and only foreground blocks can be roots
-                int *sb = stat + 5 * b;
-                sb[0] = 0x7fffffff; sb[1] = 0x7fffffff; sb[2] = -1; sb[3] = -1; sb[4] = 0;
-            }
+            M.parent[b] = (typename CclMem<COMPACT>::PT)(c ? b - lane + start_lane : CclMem<COMPACT>::kNone);
+            if (c) M.stat_init(b);
         }
+        const unsigned fg = __ballot_sync(0xffffffffu, c != 0);
+        if (c) my_list[n_fg + __popc(fg & ((1u << lane) - 1u))] = (unsigned short)(b | (lane == 0 ? 0x8000 : 0));
+        n_fg += __popc(fg);
     }
     __syncthreads();
 
     // 2. merge with the raster-preceding neighbour blocks: north, north-west, north-east, and west across a warp
     //    segment boundary (lane 0 could not see its west neighbour in step 1)
-    run_by = by_first; run_bx = bx_first;
-    for (int b = tid; b < nb; b += nt) {
+    for (int k = lane; k < n_fg; k += 32) {
+        const int e = my_list[k], b = e & 0x7fff;
         const int c = code[b];
-        const int by = run_by, bx = run_bx;
-        COVA_CCL_ADVANCE(run_by, run_bx);
-        if (!c) continue;
+        const int by = A.nbx > 1 ? (int)fast_div((uint32_t)b, A.div_nbx) : b, bx = b - by * A.nbx;
         const int cw = bx > 0 ? code[b - 1] : 0;
         const bool west_b = (c & 0x5) && (cw & 0xA);                                           // b-1 ~ b along the row
-        if (lane == 0 && west_b) uf_union(parent, b, b - 1);
+        if ((e & 0x8000) && west_b) M.unite(b, b - 1);
         if (by > 0) {
             const int u = b - A.nbx;
             const int cu = code[u];
@@ -180,31 +282,25 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             const bool do_n = n && !(n_w && west_u);
             const bool nw = (c & 0x1) && (cuw & 0x8) && !(n && west_u) && !n_w;
             const bool ne = (c & 0x2) && (cue & 0x4) && !(n && west_ue);
-            if (do_n) uf_union(parent, b, u);
-            if (nw) uf_union(parent, b, u - 1);
-            if (ne) uf_union(parent, b, u + 1);
+            if (do_n) M.unite(b, u);
+            if (nw) M.unite(b, u - 1);
+            if (ne) M.unite(b, u + 1);
         }
     }
     __syncthreads();
 
     // 3. flatten + per-root statistics.  parent[b] is lowered to the root while other threads may still walk through b in
-    //    their own uf_find: they read either b's old parent (an ancestor) or its root and reach the same root either way.
-    //    The update is an atomicMin like the links of step 2 (the root is the smallest index on the path), which keeps
-    //    every concurrent access to parent[] an atomic or a volatile load (compute-sanitizer --tool racecheck: clean).
-    run_by = by_first; run_bx = bx_first;
-    for (int b = tid; b < nb; b += nt) {
+    //    their own find: they read either b's old parent (an ancestor) or its root and reach the same root either way.
+    //    (compute-sanitizer --tool racecheck: clean.)
+    for (int k = lane; k < n_fg; k += 32) {
+        const int b = my_list[k] & 0x7fff;
         const int c = code[b];
-        const int by = run_by, bx = run_bx;
-        COVA_CCL_ADVANCE(run_by, run_bx);
-        if (!c) continue;
-        int r = uf_find(parent, b);
-        atomicMin(&parent[b], r);
-        int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
-        int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
-        int *sr = stat + 5 * r;
-        atomicMin(&sr[0], x0); atomicMax(&sr[2], x1);
-        atomicMin(&sr[1], y0); atomicMax(&sr[3], y1);
-        atomicAdd(&sr[4], __popc(c));
+        const int by = A.nbx > 1 ? (int)fast_div((uint32_t)b, A.div_nbx) : b, bx = b - by * A.nbx;
+        const int r = M.find(b);
+        M.lower(b, r);
+        const int x0 = 2 * bx + ((c & 0x5) ? 0 : 1), x1 = 2 * bx + ((c & 0xA) ? 1 : 0);
+        const int y0 = 2 * by + ((c & 0x3) ? 0 : 1), y1 = 2 * by + ((c & 0xC) ? 1 : 0);
+        M.stat_add(r, x0, y0, x1, y1, __popc(c));
     }
     __syncthreads();
 
@@ -213,7 +309,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     const int b0 = min(tid * ipt, nb), b1 = min(b0 + ipt, nb);
     int cnt = 0;
     for (int b = b0; b < b1; b++)
-        if (parent[b] == b) cnt += 0x10000 + (stat[5 * b + 4] >= A.area_thresh ? 1 : 0);
+        if ((int)M.parent[b] == b) cnt += 0x10000 + (M.stat_area(b) >= A.area_thresh ? 1 : 0);
     int incl = cnt;
     const int wid = tid >> 5;
 #pragma unroll
@@ -256,12 +352,13 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     int32_t *st = A.stats ? A.stats + (size_t)frame * (nb + 1) * 5 : nullptr;
     if (st && tid < 5) st[tid] = 0;
 
-    // 6. emit boxes in label order; turn area[] into the root -> label map
+    // 6. emit boxes in label order; turn the area slot into the root -> label map
     int rank_all = excl >> 16, rank_keep = excl & 0xffff;
     for (int b = b0; b < b1; b++) {
-        if (parent[b] != b) continue;
-        int *sb = stat + 5 * b;
-        int x0 = sb[0], y0 = sb[1], w = sb[2] - x0 + 1, h = sb[3] - y0 + 1, ar = sb[4];
+        if ((int)M.parent[b] != b) continue;
+        int x0, y0, x1, y1;
+        M.stat_get(b, x0, y0, x1, y1);
+        const int w = x1 - x0 + 1, h = y1 - y0 + 1, ar = M.stat_area(b);
         rank_all++;
         if (st) {
             int32_t *s5 = st + (size_t)rank_all * 5;
@@ -280,7 +377,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
             }
             rank_keep++;
         }
-        sb[4] = rank_all;                    // the area slot becomes the root -> label map
+        M.set_label(b, rank_all);
     }
     if (!A.labels) return;
     __syncthreads();
@@ -288,7 +385,7 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
     for (int p = tid; p < A.H * A.W; p += nt) {
         int y = p / A.W, x = p - y * A.W;
         int b = (y >> 1) * A.nbx + (x >> 1);
-        lab[p] = (m[p] != 0) ? stat[5 * parent[b] + 4] : 0;
+        lab[p] = (m[p] != 0) ? M.label((int)M.parent[b]) : 0;
     }
 }
 

@@ -237,6 +237,7 @@ struct CclBuffers {
     int32_t *d_labels = nullptr, *d_stats = nullptr, *d_nlabels = nullptr;
     size_t smem = 0;
     int threads = 0;
+    bool compact = false;     // 13-byte-per-block shared-memory layout (ccl.cuh): two CTAs per SM at 4K
 };
 
 constexpr int kCclSmemLimit = tc::kSmemLimit - 1024;   // dynamic part: the kernel also has a few bytes of static shared memory
@@ -244,8 +245,15 @@ constexpr int kCclSmemLimit = tc::kSmemLimit - 1024;   // dynamic part: the kern
 static int ccl_alloc(CclBuffers &b, int H, int W, int max_masks, bool own_masks) {
     b.H = H; b.W = W; b.nbx = (W + 1) / 2; b.nby = (H + 1) / 2; b.nb = b.nbx * b.nby; b.max_masks = max_masks;
     b.threads = ccl_threads_for(b.nb);
-    b.smem = ccl_smem_bytes(b.nb, b.threads);
-    if (b.smem > (size_t)kCclSmemLimit || b.nb >= 0xFFFF)
+    // The compact layout would give 4K masks two CTAs per SM (204 KB -> 106 KB), but measured it does not pay: its
+    // compare-and-swap statistics cost more than the second CTA brings (4K network masks 0.40 -> 0.44 ms per 1024, dense
+    // 0.83 -> 0.86; only empty / all-ones masks gain).  It is used where the wide layout does not fit at all.
+    b.compact = false;
+    static const char *force = getenv("COVA_CCL_COMPACT");         // development knob: "0" / "1"
+    if (force && (force[0] == '0' || force[0] == '1')) b.compact = force[0] == '1';
+    b.smem = ccl_smem_bytes(b.nb, b.threads, b.compact);
+    if (b.smem > (size_t)kCclSmemLimit && !b.compact) { b.compact = true; b.smem = ccl_smem_bytes(b.nb, b.threads, true); }
+    if (b.smem > (size_t)kCclSmemLimit || b.nb >= 0x7FFF)       // block indices travel in 15 bits of the foreground lists
         return set_err(COVA_E_UNSUPPORTED, "mask grid too large for the shared-memory CCL kernel");
     b.blob_cap = (size_t)max_masks * (8 + 24 * (size_t)b.nb);
     if (own_masks) COVA_CUDA(cudaMalloc(&b.d_masks, (size_t)max_masks * H * W));
@@ -281,8 +289,9 @@ static int ccl_launch(CclBuffers &b, const uint8_t *d_masks, int n, uint32_t cc_
     // the attribute is per function AND per device, last write wins: handles of different grids (or on different devices,
     // or on different threads) share ccl_bbox_kernel, so it is set for every launch and always to the same value, the
     // architectural maximum (see tc::try_launch)
-    COVA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemLimit));
-    COVA_CUDA(launch_pdl(ccl_bbox_kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, pdl, a));
+    auto kernel = b.compact ? ccl_bbox_kernel<true> : ccl_bbox_kernel<false>;
+    COVA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCclSmemLimit));
+    COVA_CUDA(launch_pdl(kernel, dim3((unsigned)n), dim3((unsigned)b.threads), b.smem, st, pdl, a));
     return COVA_OK;
 }
 
