@@ -2,12 +2,14 @@
 """Development aid: per-SOURCE-LINE stall samples and instruction counts of one kernel from an ncu capture taken with
 --import-source on.  ncu's CSV source page is per SASS instruction; the line table comes from `nvdisasm -g` of the same
 library (instruction k of the function in both listings is the same instruction).
-usage: python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTRING [LIBRARY.so] [min_pct]"""
+usage: python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTRING [LIBRARY.so] [min_pct] [SUBSTRING_IN_THE_DISASSEMBLY]
+(the two tools print template arguments differently: "(int)2, (int)32" in the report, "2, 32" in c++filt's output)"""
 import csv, os, re, subprocess, sys, tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
 so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cova_b200", "libcova_b200.so")
 min_pct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.5
+dis_kern = sys.argv[5] if len(sys.argv) > 5 else kern
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 # several kernels may be in the report: take the first block whose name matches
@@ -33,7 +35,7 @@ for l in dis:
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
     if m:
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-        on = kern in name and (want is None or want == name)
+        on = dis_kern in name and (want is None or want == name)
         if on:
             want = name
         continue
