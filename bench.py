@@ -416,6 +416,30 @@ def main():
                          "d2h_bytes_per_step": e2e_packed["d2h_bytes_per_step"],
                          "path": "packed16 frames already packed in pinned host memory (producer-side packing; NOT the reference's buffer format)"}
 
+    # ---- the drop-in ELEMENT calls (one buffer per call, host memory in and out, as the GStreamer elements make them):
+    # slow by construction - a host<->device round trip and a synchronisation per frame - and timed here so that the cost
+    # of staying on the per-buffer interface is a number, not a guess
+    shims = None
+    if rank == 0:
+        from cova_b200.elements import BboxCc, MetaPreprocess
+        mp, cc = MetaPreprocess(w_mb * 16, h_mb * 16, T, 1, device=local_rank), BboxCc(w_mb, h_mb, 1, device=local_rank)
+        one = frames_np[0]
+        msk = (np.random.default_rng(0).random((h_mb, w_mb)) < 0.08).astype(np.uint8)
+        for f in range(8):
+            mp.transform(one[f % one.shape[0]]); cc.transform_ip(msk)
+        n_el = 200
+        t0 = time.perf_counter()
+        for f in range(n_el):
+            mp.transform(one[f % one.shape[0]])
+        t_mp = (time.perf_counter() - t0) / n_el
+        t0 = time.perf_counter()
+        for f in range(n_el):
+            cc.transform_ip(msk)
+        t_cc = (time.perf_counter() - t0) / n_el
+        shims = {"metapreprocess_transform_us": round(t_mp * 1e6, 1), "bboxcc_transform_ip_us": round(t_cc * 1e6, 1),
+                 "note": "per buffer through the element interface (ctypes call included); the batch path above is the fast one"}
+        mp.close(); cc.close()
+
     if rank == 0:
         pk = peaks()
         # Which tensor peak applies: MEASURED_PEAKS.json holds a burst figure (cuBLAS timed alone, clocks near maximum) and
@@ -504,7 +528,7 @@ def main():
                        "weights": f"random-init (seed 0, head bias {head_bias}), reference architecture",
                        "host_numa": numa},
             "e2e": e2e_best, "e2e_paths": e2e_paths,
-            "gpu_launches": int(launches), "roofline": roof, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": int(launches), "roofline": roof, "stages": stages, "element_shims": shims, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -349,13 +349,15 @@ extern "C" int cova_bboxcc_transform_ip(cova_bboxcc *cc, const uint8_t *mask, si
     COVA_CUDA(cudaMemcpyAsync(cc->b.d_masks, mask, mask_len, cudaMemcpyHostToDevice, cc->stream));
     int rc = ccl_launch(cc->b, cc->b.d_masks, 1, cc->cc_threshold, false, cc->stream);
     if (rc) return rc;
+    // One synchronisation per buffer: the length and as much of the blob as the caller's buffer (or the worst case of this
+    // grid) can hold travel back together; the single mask's blob starts at offset 0 of the arena.
     unsigned long long len = 0;
+    const size_t spec = out ? std::min(out_cap, cc->b.blob_cap) : 0;
     COVA_CUDA(cudaMemcpyAsync(&len, cc->b.d_lens, sizeof(len), cudaMemcpyDeviceToHost, cc->stream));
+    if (spec) COVA_CUDA(cudaMemcpyAsync(out, cc->b.d_blob, spec, cudaMemcpyDeviceToHost, cc->stream));
     COVA_CUDA(cudaStreamSynchronize(cc->stream));
     *out_len = (size_t)len;
     if (!out || out_cap < len) return set_err(COVA_E_TOOSMALL, "serialized boxes need a larger buffer");
-    COVA_CUDA(cudaMemcpyAsync(out, cc->b.d_blob, len, cudaMemcpyDeviceToHost, cc->stream));
-    COVA_CUDA(cudaStreamSynchronize(cc->stream));
     return COVA_OK;
 }
 
