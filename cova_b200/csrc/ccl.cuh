@@ -323,19 +323,37 @@ __global__ void ccl_bbox_kernel(CclArgs A) {
         __syncthreads();
         // 2b. links across tile borders, by the concurrent union-find: the first row of every row of tiles (north, north-west,
         //     north-east), the first column of every column of tiles (west, north-west), the last column (north-east)
-        for (int k = lane; k < n_fg; k += 32) {
-            const int b = my_list[k] & 0x7fff;
-            const int c = code[b];
-            const int by = A.nbx > 1 ? (int)fast_div((uint32_t)b, A.div_nbx) : b, bx = b - by * A.nbx;
-            const bool col0 = bx > 0 && (bx & 31) == 0, col31 = (bx & 31) == 31 && bx + 1 < A.nbx;
-            const bool row0 = by > 0 && (A.tile_rows == 1 || by - (int)fast_div((uint32_t)by, A.div_tile_rows) * A.tile_rows == 0);
-            if (!(col0 || col31 || row0)) continue;
-            if (col0 && (c & 0x5) && (code[b - 1] & 0xA)) M.unite(b, b - 1);
-            if (by > 0) {
-                const int u = b - A.nbx;
-                if (row0 && (c & 0x3) && (code[u] & 0xC)) M.unite(b, u);
-                if ((row0 || col0) && bx > 0 && (c & 0x1) && (code[u - 1] & 0x8)) M.unite(b, u - 1);
-                if ((row0 || col31) && bx + 1 < A.nbx && (c & 0x2) && (code[u + 1] & 0x4)) M.unite(b, u + 1);
+        //     The border blocks are enumerated by geometry (a few hundred of the thousands of foreground blocks; walking the
+        //     whole foreground list for them cost a quarter of the kernel on dense 4K masks): first the rows that start a row
+        //     of tiles, then the two columns on either side of every vertical tile border.
+        {
+            const int n_row = (A.tiles_y - 1) * A.nbx, n_col = (A.tiles_x - 1) * 2 * A.nby;
+            for (int i = tid; i < n_row + n_col; i += nt) {
+                int by, bx;
+                bool row0 = false, col0 = false, col31 = false;
+                if (i < n_row) {
+                    const int t = A.nbx > 1 ? (int)fast_div((uint32_t)i, A.div_nbx) : i;
+                    by = (t + 1) * A.tile_rows; bx = i - t * A.nbx;
+                    row0 = true;
+                    col0 = bx > 0 && (bx & 31) == 0; col31 = (bx & 31) == 31 && bx + 1 < A.nbx;
+                } else {
+                    const int e = i - n_row, t = e / (2 * A.nby), rem = e - t * 2 * A.nby;      // one division per border block
+                    by = rem >> 1;
+                    bx = (t + 1) * 32 - (rem & 1);                                              // column 31 of tile t, column 0 of tile t+1
+                    if (rem & 1) col31 = bx + 1 < A.nbx; else col0 = true;
+                    if (by > 0 && (A.tile_rows == 1 || by - (int)fast_div((uint32_t)by, A.div_tile_rows) * A.tile_rows == 0)) continue;   // done as a row block
+                }
+                if (by >= A.nby || bx >= A.nbx) continue;
+                const int b = by * A.nbx + bx;
+                const int c = code[b];
+                if (!c) continue;
+                if (col0 && (c & 0x5) && (code[b - 1] & 0xA)) M.unite(b, b - 1);
+                if (by > 0) {
+                    const int u = b - A.nbx;
+                    if (row0 && (c & 0x3) && (code[u] & 0xC)) M.unite(b, u);
+                    if ((row0 || col0) && bx > 0 && (c & 0x1) && (code[u - 1] & 0x8)) M.unite(b, u - 1);
+                    if ((row0 || col31) && bx + 1 < A.nbx && (c & 0x2) && (code[u + 1] & 0x4)) M.unite(b, u + 1);
+                }
             }
         }
         __syncthreads();
