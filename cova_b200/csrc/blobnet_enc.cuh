@@ -343,16 +343,16 @@ __global__ void __launch_bounds__(C::THREADS, 1) enc_ws_kernel(const __grid_cons
         // pass as they complete, interleaved with the finalisation of tile i out of registers - so the MMA warp never
         // waits for a finalisation and the epilogue never waits for a pass it could have had earlier.
         uint32_t slot_it = 0;
-        int g_next = cta, jt_next = 0;
+        // this CTA's tiles in order: groups cta, cta + n_cta, ... of TPS consecutive tiles; only the last group of the launch
+        // can be partial, so the first tile index beyond n_tiles ends the sequence (the producer and the MMA warp walk the
+        // same sequence).  Kept to a handful of instructions: the first version of this iterator was 11 % of the kernel's
+        // warp instructions (profiles/r2v_enc2_lines.txt).
+        int g_next = cta, jt_next = 0, t_next = cta * C::TPS;
         auto next_tile = [&]() -> int {
-            while (g_next < p.n_groups) {
-                if (jt_next < C::TPS) {
-                    const int t = g_next * C::TPS + jt_next++;
-                    if (t < p.n_tiles) return t;
-                }
-                g_next += n_cta; jt_next = 0;
-            }
-            return -1;
+            if (g_next >= p.n_groups || t_next >= p.n_tiles) { g_next = p.n_groups; return -1; }
+            const int t = t_next;
+            if (++jt_next == C::TPS) { jt_next = 0; g_next += n_cta; t_next = g_next * C::TPS; } else { t_next++; }
+            return t;
         };
         float run_cur[C::MAXU][C::NIT][4];
         uint32_t cur_o = 0, cur_s = 0, cur_vmask = 0, cur_vmine = 0;   // cur_vmine: validity bits of this thread's pixel of every unit
