@@ -629,3 +629,23 @@ def test_packed_input_needs_an_even_width():
     with pytest.raises(_lib.CovaError) as e:
         BlobPipeline(37, 21, weights.to_blob(weights.random_weights(0)), 1, 8, packed_input=True)
     assert e.value.code == _lib.E_UNSUPPORTED
+
+
+def test_bboxcc_random_shapes_against_the_c_oracle():
+    """Element-level CCL on 40 random grids (odd and even extents from 1 to 150, the tile-scan path above 4096 blocks
+    included), random densities: labels, statistics and the serialized boxes equal the C oracle."""
+    rng = np.random.default_rng(11)
+    shapes = [(1, 1), (1, 2), (2, 1), (3, 200), (200, 3), (129, 130), (135, 240), (150, 150)]
+    shapes += [(int(rng.integers(1, 151)), int(rng.integers(1, 151))) for _ in range(32)]
+    for h, w in shapes:
+        m = (rng.random((h, w)) < rng.uniform(0.05, 0.9)).astype(np.uint8)
+        el = BboxCc(w, h, 1)
+        n, labels, stats = el.labels(m)
+        n2, l2, s2 = c_oracle.ccl(m)
+        assert n == n2 and (labels == l2).all(), (h, w)
+        if n > 1:
+            assert (stats[1:] == s2[1:]).all(), (h, w)
+        for thr in (1, 5):
+            el.set_property("cc-threshold", thr)
+            assert el.transform_ip(m) == bboxcc_ref.bboxcc_transform_ref(m, w, h, thr), (h, w, thr)
+        el.close()
