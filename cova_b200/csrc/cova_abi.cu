@@ -424,7 +424,8 @@ struct cova_pipeline {
     // per-stream state for CONTINUED batches (metapreprocess/imp.rs:38-42: prev_buffers and gamma_idx live as long as the
     // stream): the last T - 1 frames of every stream id on the device, frames seen so far on the host
     uint8_t *d_carry = nullptr;
-    std::vector<uint64_t> n_seen;
+    std::vector<uint64_t> n_seen, id_mark;
+    uint64_t id_epoch = 0;
     // A batch is processed in chunks of whole chains: the activation buffers are sized for ONE chunk, and
     // process_host() overlaps the H2D copy of chunk c+1, the kernels of chunk c and the D2H of chunk c-1.
     uint32_t chunk_streams = 0;          // chains per chunk (capacity)
@@ -1222,13 +1223,14 @@ static int submit_impl(cova_pipeline *p, const uint8_t *frames, uint32_t n_strea
     uint32_t h = 0, first = t1;
     if (stateful) {
         if (!fps) return set_err(COVA_E_INVAL, "a stream batch needs at least one frame per stream");
+        if (p->n_seen.empty()) { p->n_seen.assign(p->max_streams, 0); p->id_mark.assign(p->max_streams, 0); }
+        p->id_epoch++;                                              // "seen in this batch" marks without clearing the array
         for (uint32_t s = 0; s < n_streams; s++) {
             const uint32_t id = stream_ids ? stream_ids[s] : s;
             if (id >= p->max_streams) return set_err(COVA_E_INVAL, "stream id out of range (ids are 0 .. max_streams-1)");
-            for (uint32_t s2 = 0; stream_ids && s2 < s; s2++)
-                if (stream_ids[s2] == id) return set_err(COVA_E_INVAL, "a stream id appears twice in one batch");
+            if (p->id_mark[id] == p->id_epoch) return set_err(COVA_E_INVAL, "a stream id appears twice in one batch");
+            p->id_mark[id] = p->id_epoch;
         }
-        if (p->n_seen.empty()) p->n_seen.assign(p->max_streams, 0);
         if (flags & COVA_SUBMIT_CONTINUE) {
             // the kernels take one window shape per batch: every chain must carry the same number of frames and sit at the
             // same gamma phase, i.e. the streams of a batch advance in lock-step (start new streams in a batch of their own)

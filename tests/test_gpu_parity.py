@@ -649,3 +649,24 @@ def test_bboxcc_random_shapes_against_the_c_oracle():
             el.set_property("cc-threshold", thr)
             assert el.transform_ip(m) == bboxcc_ref.bboxcc_transform_ref(m, w, h, thr), (h, w, thr)
         el.close()
+
+
+def test_stream_continuity_many_streams_in_chunks():
+    """Continued batches with the library's chunking on (three chunks of whole chains per batch, the last one smaller) and a
+    permuted stream-id table: 26 streams x 57 frames fed as 19 + 19 + 19 must equal the single submit, stream by stream."""
+    wts = weights.random_weights(0, head_bias=-1.0)
+    frames = synth.tiled_streams(26, 57, 45, 80, config_idx=14, n_unique=13)
+    p = BlobPipeline(80, 45, weights.to_blob(wts), 26, 57, n_chunks=3)
+    whole = p.process(frames)
+    wps = len(whole) // 26
+    ids = np.random.default_rng(5).permutation(26).astype(np.uint32)
+    got = {int(i): [] for i in ids}
+    for k in range(3):
+        p.submit(frames[:, 19 * k: 19 * (k + 1)], stream_ids=ids, cont=k > 0)
+        boxes, wid, _ = p.collect(meta=True)
+        w = len(boxes) // 26
+        assert w == (16 if k == 0 else 19) and (wid == np.repeat(ids, w)).all()
+        for s, sid in enumerate(ids):
+            got[int(sid)] += boxes[s * w: (s + 1) * w]
+    for s, sid in enumerate(ids):
+        assert got[int(sid)] == whole[s * wps: (s + 1) * wps], s
