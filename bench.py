@@ -10,6 +10,7 @@ A step = one pass of the whole path over one batch of independent chains of 67 f
     --config c3            1080p, 120x68, 64 chains per GPU = 4096 windows per step (configs[2]: 256 streams over 4 GPUs)
     --config c4            4K,    240x135, 16 chains per GPU = 1024 windows per step, dense worst case (configs[3]:
                            head bias 0 -> about half of the mask is foreground, thousands of components per frame)
+    --config c5            = c2 (configs[4]: 1024 concurrent 720p streams over 8 GPUs = 128 chains per GPU; run with --gpus 8)
 `value` counts detections (output windows) per second with the frames resident in HBM; `e2e` is the same through
 BlobPipeline.submit()/collect() with pinned host frames in and bincode boxes out.  Prints ONE JSON line (rank 0).
 """
@@ -33,7 +34,9 @@ FRAMES_PER_STREAM = 67
 # name -> (h_mb, w_mb, chains per GPU, head bias of the random-init weights, description)
 CONFIGS = {"c2": (45, 80, 128, -1.0, "synthetic 720p metadata (80x45 MB grid)"),
            "c3": (68, 120, 64, -1.0, "synthetic 1080p metadata (120x68 MB grid)"),
-           "c4": (135, 240, 16, 0.0, "synthetic 4K metadata (240x135 MB grid), dense worst case")}
+           "c4": (135, 240, 16, 0.0, "synthetic 4K metadata (240x135 MB grid), dense worst case"),
+           # BASELINE.json configs[4] (1024 concurrent 720p streams over 8 GPUs) is the c2 workload run with --gpus 8
+           "c5": (45, 80, 128, -1.0, "synthetic 720p metadata (80x45 MB grid), 1024 streams over 8 GPUs = 128 per GPU")}
 H_MB, W_MB, STREAMS_PER_GPU = CONFIGS["c2"][:3]   # the default workload
 METRIC, UNIT = "blob_detection_frames_per_sec", "frames/s"
 # kernels of one step in launch order: (name the library reports, bound, BlobNet layer it belongs to)
@@ -453,7 +456,7 @@ def main():
         work, fl = kernel_work(h_mb, w_mb, nbox)
         lbytes = layer_bytes(h_mb, w_mb)
         traffic, traffic_file = {}, None
-        for cand in (f"traffic_{args.config}.json", "traffic.json"):
+        for cand in (f"traffic_{'c2' if args.config == 'c5' else args.config}.json", "traffic.json"):
             tpath = os.path.join(ROOT, "profiles", cand)
             if os.path.exists(tpath):
                 tj = json.load(open(tpath))
