@@ -140,3 +140,29 @@ def test_frame_packer_is_exact(threads):
         assert (got == want).all(), n
     fr = synth.synth_streams(2, 5, 45, 80, config_idx=1)
     assert pk.pack(fr).shape == fr.shape[:-1]
+
+
+def test_python_constants_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "cova_b200.h")).read()
+
+    def define(name):
+        m = re.search(r"#define\s+" + name + r"\s+\(?(-?0x[0-9a-fA-F]+|-?\d+)u?\)?", hdr)
+        assert m, name
+        return int(m.group(1), 0)
+
+    assert define("COVA_FLAG_KEEP_LOGITS") == _lib.FLAG_KEEP_LOGITS and define("COVA_FLAG_KEEP_STACKED") == _lib.FLAG_KEEP_STACKED
+    assert define("COVA_FLAG_INPUT_PACKED16") == _lib.FLAG_INPUT_PACKED16 and define("COVA_SUBMIT_CONTINUE") == _lib.SUBMIT_CONTINUE
+    assert define("COVA_IMPL_TCGEN05") == _lib.IMPL_TCGEN05 and define("COVA_IMPL_SIMT") == _lib.IMPL_SIMT
+    for name, val in (("OK", _lib.OK), ("DROPPED", _lib.DROPPED), ("E_INVAL", _lib.E_INVAL), ("E_CUDA", _lib.E_CUDA), ("E_NOMEM", _lib.E_NOMEM),
+                      ("E_TOOSMALL", _lib.E_TOOSMALL), ("E_WEIGHTS", _lib.E_WEIGHTS), ("E_UNSUPPORTED", _lib.E_UNSUPPORTED),
+                      ("E_NODEVICE", _lib.E_NODEVICE), ("E_NUMERIC", _lib.E_NUMERIC), ("E_STATE", _lib.E_STATE)):
+        assert define("COVA_" + name) == val, name
+    # packed input is refused for odd widths and together with KEEP_STACKED before any device is touched
+    lib = _lib.load()
+    blob = weights.to_blob(weights.random_weights(0))
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    h = ctypes.c_void_p()
+    args = (ctypes.byref(h), 0, 37, 21, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1)
+    assert lib.cova_pipeline_new(*args, _lib.FLAG_INPUT_PACKED16) == _lib.E_UNSUPPORTED
+    args = (ctypes.byref(h), 0, 80, 45, 4, 1, 1, 8, ctypes.cast(buf, ctypes.c_void_p), len(blob), 1)
+    assert lib.cova_pipeline_new(*args, _lib.FLAG_INPUT_PACKED16 | _lib.FLAG_KEEP_STACKED) == _lib.E_INVAL
