@@ -670,3 +670,21 @@ def test_stream_continuity_many_streams_in_chunks():
             got[int(sid)] += boxes[s * w: (s + 1) * w]
     for s, sid in enumerate(ids):
         assert got[int(sid)] == whole[s * wps: (s + 1) * wps], s
+
+
+def test_grid_limits_are_reported_not_crashed():
+    """The shared-memory CCL holds one mask per CTA: a grid beyond its capacity (8K video: 480x270 macroblocks = 32,400
+    blocks) is refused with COVA_E_UNSUPPORTED at creation; the largest supported class (150x150, tile-scan path) runs the
+    whole path and matches the oracle's boxes."""
+    blob = weights.to_blob(weights.random_weights(0, head_bias=-0.5))
+    with pytest.raises(_lib.CovaError) as e:
+        BlobPipeline(480, 270, blob, 1, 4)
+    assert e.value.code == _lib.E_UNSUPPORTED
+    with pytest.raises(_lib.CovaError) as e:
+        BboxCc(480, 270, 1)
+    assert e.value.code == _lib.E_UNSUPPORTED
+    frames = synth.synth_streams(1, 5, 150, 150, config_idx=40)
+    p = BlobPipeline(150, 150, blob, 1, 5)
+    boxes = p.process(frames)
+    mask = p.read_mask()
+    assert len(boxes) == 2 and boxes == c_oracle.bboxcc_batch(mask, 1)
